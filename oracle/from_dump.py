@@ -68,7 +68,14 @@ def mesh_from_dump(p, man, get, geom_override=None):
             geom, gshape = geom_override(mb)
         else:
             geom, gshape = geom_from_dump(get, gid, shape)
-        b = Block(p, mb["xmin"], mb["dx"], block_bc(p, mb), mb["lx"], geom, gshape)
+        # logical position from coordinates (loc.lx* is per-tree in Parthenon's forest)
+        mesh_min = [man["mesh"]["x%dmin" % (d + 1)] for d in range(3)]
+        lx = []
+        for d in range(3):
+            g = p["ng"] if d < p["ndim"] else 0
+            x0 = mb["xmin"][d] + g * mb["dx"][d]
+            lx.append(int(round((x0 - mesh_min[d]) / (p["nx"][d] * mb["dx"][d]))))
+        b = Block(p, mb["xmin"], mb["dx"], block_bc(p, mb), lx, geom, gshape)
         load_state(b, get, gid, shape)
         blocks.append(b)
     periodic = [p["mesh_bc"][2 * d] == "periodic" for d in range(3)]

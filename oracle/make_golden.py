@@ -1,0 +1,83 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE ONLY — regenerates tests/golden/*.npz by running the UNMODIFIED
+reference (oracle/_ref/ref_dump_{mink,fmks}, built by oracle/build_ref.sh from
+/root/reference) on small versions of BASELINE.json's configs and packing the per-stage
+field dumps. Every fixture is self-checked against the oracle restatement before it is
+written. Run from the repo root: python oracle/make_golden.py
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import deck as deckmod  # noqa: E402
+from oracle import refdump  # noqa: E402
+
+B3 = lambda n1, n2, n3, b1, b2, b3: [
+    "parthenon/mesh/nx1=%d" % n1, "parthenon/mesh/nx2=%d" % n2, "parthenon/mesh/nx3=%d" % n3,
+    "parthenon/meshblock/nx1=%d" % b1, "parthenon/meshblock/nx2=%d" % b2, "parthenon/meshblock/nx3=%d" % b3]
+
+# name -> (binary, deck, overrides, nlim, geometry kind)
+CASES = {
+    # configs[0]: 1-D SR MHD shocktube, weno5 + hll, gr_outflow BCs
+    "shocktube": ("mink", "mhd_shocktube", ["parthenon/mesh/nx1=64", "parthenon/time/dt_init_fact=1.0"], 3, 0),
+    # configs[1] (2-D slice, 4 blocks, periodic halos): MHD fast mode, linear + hll, c2p_tol 1e-12
+    "linmodes2d": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast"]
+                   + B3(16, 16, 1, 8, 8, 1), 2, 0),
+    # configs[2]: 3-D blast wave, mp5 + llf, MHD on, ceilings active (one periodic 8^3 block)
+    "blast3d": ("mink", "blast_wave_3d", B3(8, 8, 8, 8, 8, 8) + [
+        "parthenon/mesh/refinement=none", "fluid/mhd=true", "fixup/enable_floors=true",
+        "fixup/floor_type=ConstantRhoSie", "fixup/rho0_floor=1e-2", "fixup/sie0_floor=0.5",
+        "fixup/enable_c2p_fixup=true", "fixup/enable_ceilings=true", "fixup/sie0_ceiling=50",
+        "fixup/gam0_ceiling=1.0001", "fixup/enable_mhd_floors=true", "sedov/rinner=0.4",
+        "sedov/explosion_energy=1", "parthenon/time/dt_init_fact=1.0"], 4, 0),
+    # configs[3] (2-D slice): FM torus in FMKS, weno5 + llf, primitive BCs, floors/ceilings/fixups;
+    # c2p_floor_scale_fac < 1 makes ApplyFloors fire (thousands of zones per stage)
+    "torus2d": ("fmks", "torus", B3(32, 16, 1, 16, 8, 1) + [
+        "torus/seed=7", "torus/u_jitter=0", "fluid/c2p_floor_scale_fac=0.1",
+        "parthenon/time/dt_init_fact=1e-2"], 3, 1),
+}
+# larger live-only cases (tests/test_ref_live.py runs these when oracle/_ref exists)
+LIVE = {
+    "linmodes3d": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast", "fluid/recon=weno5"]
+                   + B3(16, 16, 16, 8, 8, 8), 3, 0),
+    "torus3d": ("fmks", "torus", B3(32, 16, 8, 16, 8, 8) + [
+        "torus/seed=7", "torus/u_jitter=0", "fluid/c2p_floor_scale_fac=0.1",
+        "parthenon/time/dt_init_fact=1e-2"], 12, 1),
+}
+
+
+def run_ref(case, outdir, qlqr=False):
+    binary, deck, ov, nlim, _ = case
+    env = dict(os.environ, REF_DUMP_DIR=outdir, OMP_NUM_THREADS="1")
+    if qlqr:
+        env["REF_DUMP_QLQR"] = "1"
+    exe = os.path.join(HERE, "_ref", "ref_dump_" + binary)
+    deckf = os.path.join(HERE, "_ref", "decks", deck + ".pin")
+    with open(os.path.join(outdir, "log.txt"), "w") as log:
+        subprocess.check_call([exe, "-i", deckf] + ov + ["parthenon/time/nlim=%d" % nlim], cwd=outdir, env=env,
+                              stdout=log, stderr=subprocess.STDOUT)
+    return ["init"] + ["c%04ds%d" % (c, s) for c in range(nlim) for s in (1, 2)]
+
+
+def main():
+    gold = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+    for name, case in CASES.items():
+        tmp = tempfile.mkdtemp(prefix="gold_" + name)
+        tags = run_ref(case, tmp)
+        out = os.path.join(gold, name + ".npz")
+        with open(os.path.join(HERE, "_ref", "decks", case[1] + ".pin")) as f:
+            blocks = deckmod.parse_deck(f.read(), case[2])
+        refdump.pack_golden(tmp, tags, out, extra_meta={"deck_blocks": blocks, "deck": case[1], "overrides": case[2], "nlim": case[3],
+                                                         "geometry": case[4], "binary": case[0]})
+        shutil.rmtree(tmp)
+        print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
+
+
+if __name__ == "__main__":
+    main()
