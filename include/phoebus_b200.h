@@ -1,0 +1,202 @@
+/* phoebus_b200 — C ABI of the B200-native GRMHD fluid-update path.
+ *
+ * Every entry point is one Parthenon/Phoebus task (or a fusion of adjacent tasks) applied to a
+ * whole pack of MeshBlocks in one launch, asynchronously on a caller-supplied CUDA stream.
+ * Plain pointers and sizes only; nothing here depends on torch, Kokkos or Parthenon.
+ * "ref:" lines cite the reference interface (lanl/phoebus @ 830cb3ab, paths relative to the
+ * reference root) that each entry point replaces.
+ *
+ * Conventions
+ *  - All field data is FP64 in device memory, one slab per field per pack:
+ *    [block][component][k][j][i], i fastest, ghost zones (ng) in every active dimension —
+ *    per block this is exactly Parthenon's ParArrayND layout
+ *    (ref: external/parthenon/src/interface/variable.hpp:138, src/fluid/fluid.cpp:300-304).
+ *  - Component order (ref: src/fluid/fluid.cpp:272-286):
+ *      prim: p.density, p.velocity[3], p.energy, [p.bfield[3]], pressure, gamma1   (7 + 3*mhd)
+ *      cons: c.density, c.momentum[3], c.energy, [c.bfield[3]]                     (5 + 3*mhd)
+ *  - Return value: 0 on success, negative PB_E* code otherwise; pb_last_error() gives text.
+ *    Numerical failure is data (the `fail` field: 1.0 = success, 0.0 = failed zone,
+ *    ref: src/fluid/fluid.cpp:506-514), never an error code.
+ *  - Entry points never allocate field memory and never synchronise the stream, except the
+ *    *_host convenience calls, which say so.
+ */
+#ifndef PHOEBUS_B200_H_
+#define PHOEBUS_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK 0
+#define PB_EINVAL (-1)  /* bad argument / unsupported configuration */
+#define PB_ECUDA (-2)   /* CUDA runtime error (launch failure, no device) */
+
+/* geometry table: per slot [4 loc][PB_NGLOC][gk][gj][gi] then [PB_NGDER][gk][gj][gi].
+ * loc: 0 Cent, 1 Face1, 2 Face2, 3 Face3 (ref: src/phoebus_utils/cell_locations.hpp:21-37).
+ * components (ref: src/geometry/cached_system.hpp:42-52): alpha, bcon[3], gcov[10 sym],
+ * gamcon[6 sym], detgam; centre only: dalpha[3], dg[10 sym][3]. */
+#define PB_NGLOC 21
+#define PB_NGDER 33
+#define PB_GEOM_WORDS (4 * PB_NGLOC + PB_NGDER)
+
+/* boundary codes in pb_block_t.bc */
+#define PB_BC_BLOCK 0      /* neighbouring MeshBlock (filled by the halo exchange) */
+#define PB_BC_PERIODIC (-1) /* periodic mesh face (filled by the halo exchange) */
+#define PB_BC_OUTFLOW 1    /* "gr_outflow" (ref: src/phoebus_boundaries/phoebus_boundaries.cpp:118,222) */
+#define PB_BC_REFLECT 2    /* "reflect" (ref: phoebus_boundaries.cpp:44-116) */
+#define PB_BC_POLAR 3      /* "polar" (ref: phoebus_boundaries.cpp:153,187) */
+
+/* neighbour codes in pb_block_t.nbr */
+#define PB_NBR_NONE (-1)   /* physical boundary: no neighbour */
+#define PB_NBR_REMOTE (-2) /* neighbour lives on another GPU: filled by pb_halo_unpack */
+
+/* Per-MeshBlock metadata; the pack holds a device array of these. */
+typedef struct pb_block {
+  double xmin[3];  /* coordinate of cell index 0 (ghost offset included), ref: uniform_cartesian.hpp:30-36 */
+  double dx[3];
+  int bc[6];       /* ix1, ox1, ix2, ox2, ix3, ox3 */
+  int geom_slot;   /* which geometry table this block reads */
+  int floor_slot;  /* which floor table this block reads */
+  int nbr[27];     /* block index in this pack of the neighbour at offset (o1+1)+3*(o2+1)+9*(o3+1) */
+  int pad_;
+} pb_block_t;
+
+/* Flattened Params of the fluid, fixup, eos and geometry packages
+ * (ref: src/fluid/fluid.cpp:53-137, src/fixup/fixup.cpp:53-277,
+ *  src/microphysics/eos_phoebus/eos_phoebus.cpp:86-95). */
+typedef struct pb_cfg {
+  int ndim, nx[3], ng; /* interior zones per block; ghosts only in active dimensions */
+  int mhd;             /* fluid/mhd */
+  int recon;           /* 0 constant, 1 linear, 2 weno5z, 3 mp5 (ref: src/reconstruction.hpp:23) */
+  int riemann;         /* 0 llf, 1 hll (ref: src/fluid/riemann.hpp:30) */
+  double c2p_tol;
+  int c2p_max_iter;
+  double c2p_floor_scale_fac;
+  int c2p_fail_on_floors, c2p_fail_on_ceilings;
+  int floor_type;      /* 0 ConstantRhoSie 1 ExpX1RhoSie 2 ExpX1RhoU 3 X1RhoSie 4 RRhoSie (ref: fixup.hpp:59-147) */
+  double rho0, sie0, rexp, sexp, rho_min_eos, sie_min_eos;
+  double gam_max, sie_max;         /* Ceilings (ref: fixup.hpp:182-232) */
+  double bsqorho_max, bsqou_max;   /* MHDCeilings (ref: fixup.hpp:234-280) */
+  int enable_floors, enable_mhd_floors, enable_c2p_fixup, enable_flux_fixup;
+  int c2p_failure_strategy;        /* 0 interpolate, 1 floors (ref: fixup_c2p.cpp:112-122) */
+  double gm1, Cv;                  /* IdealGas (ref: singularity-eos eos_ideal.hpp:59-137) */
+  int gk, gj, gi;                  /* geometry table extents: block extent or 1 (broadcast) */
+  int bc_prim;                     /* phoebus/mesh bc_vars == primitive */
+  int ox1_inflow_check;            /* fixup/enable_ox1_fmks_inflow_check */
+} pb_cfg_t;
+
+/* A pack of MeshBlocks: device pointers to the OneCopy fields shared by all stages
+ * (ref: src/fluid/fluid.cpp:139-316). Conserved containers ("base", "1", ...) are passed
+ * per call because they are per-stage (Metadata::Independent). */
+typedef struct pb_pack {
+  int nblocks;
+  const pb_block_t *blocks; /* device [nblocks] */
+  const double *geom;       /* device [nslots][PB_GEOM_WORDS][gk][gj][gi] */
+  const double *floor_tab;  /* device [nfslots][2 loc (cell, face1)][2 (rho, sie/u)][ni] */
+  double *prim;             /* [b][nprim][cells] */
+  double *temp;             /* [b][cells]  temperature */
+  double *c2p_mu;           /* [b][cells]  root-finder guess history */
+  double *fail;             /* [b][cells] */
+  double *csig;             /* [b][ndim][cells] cell_signal_speed */
+  double *fsig;             /* [b][ndim][cells] face_signal_speed */
+  double *flux;             /* [b][ndim][ncons][cells] */
+  double *emf;              /* [b][3][cells] */
+} pb_pack_t;
+
+const char *pb_version(void);
+const char *pb_last_error(void);
+int pb_nprim(const pb_cfg_t *cfg);
+int pb_ncons(const pb_cfg_t *cfg);
+long long pb_cells_per_block(const pb_cfg_t *cfg);
+/* number of SMs of the current device (grid sizing); negative on error */
+int pb_device_sm_count(void);
+
+/* ---- host-side table builders (run on the CPU at initialisation, like the reference's
+ * Geometry::SetCachedCoordinateSystem, ref: src/geometry/cached_system.hpp:593-775) ------- */
+/* kind 0 Minkowski (ref: src/geometry/minkowski.hpp:35-115), 1 FMKS =
+ * Modified<SphericalKerrSchild, McKinneyGammieRyan> (ref: src/geometry/fmks.hpp:44).
+ * par = {a, h, xt, alpha, x0, smooth, hexp_br, hexp_nsq, hexp_csq, derefine_poles}.
+ * out_host: PB_GEOM_WORDS*gk*gj*gi doubles. */
+int pb_build_geometry_host(int kind, const double *par, const pb_cfg_t *cfg, const double xmin[3],
+                           const double dx[3], double *out_host);
+/* Floors::GetFloors tabulated along x1 (ref: src/fixup/fixup.hpp:99-147): out_host[2][2][ni] */
+int pb_build_floor_table_host(const pb_cfg_t *cfg, const double xmin[3], const double dx[3],
+                              double *out_host);
+
+/* ---- tasks ------------------------------------------------------------------------------ */
+/* ref: TaskStatus fluid::CalculateFluxes(MeshBlockData<Real>*), src/fluid/fluid.cpp:659-773.
+ * Fused reconstruction + Riemann solve per direction; writes pack->flux and pack->fsig. */
+int pb_calculate_fluxes(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream);
+/* ref: TaskStatus fluid::FluxCT(MeshBlockData<Real>*), src/fluid/fluid.cpp:775-841 */
+int pb_flux_ct(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream);
+/* ref: TaskStatus fixup::FixFluxes(MeshBlockData<Real>*), src/fixup/fixup.cpp:728-1078 */
+int pb_fix_fluxes(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream);
+/* ref: parthenon::Update::FluxDivergence<MeshData>, external/parthenon/src/interface/update.cpp:63-85 */
+int pb_flux_divergence(const pb_pack_t *pack, const pb_cfg_t *cfg, double *dudt, void *stream);
+/* ref: fluid::CalculateFluidSourceTerms(MeshData*, MeshData*), src/fluid/fluid.cpp:566-657;
+ * gsrc [b][4][cells] = sources of S1,S2,S3,tau on interior zones */
+int pb_source_terms(const pb_pack_t *pack, const pb_cfg_t *cfg, double *gsrc, void *stream);
+/* ref: parthenon::Update::WeightedSumData (SumData / AverageIndependentData /
+ * UpdateIndependentData), external/parthenon/src/interface/update.hpp:71-136:
+ * z = w1*x + w2*y over n doubles (entire arrays, ghosts included) */
+int pb_weighted_sum(const double *x, const double *y, double w1, double w2, double *z, long long n,
+                    void *stream);
+/* Fusion of FluxDivergence + CalculateFluidSourceTerms + SumData + AverageIndependentData +
+ * UpdateIndependentData (ref: src/phoebus_driver.cpp:560-576) on interior zones:
+ *   dudt = -div F (+ gsrc on momentum, energy);  uout = (beta*u0 + (1-beta)*ubase) + bdt*dudt.
+ * dudt_out / gsrc_out may be NULL (not materialised). u0 is NOT averaged in place. */
+int pb_update_fused(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *u0, const double *ubase,
+                    double beta, double bdt, double *uout, double *dudt_out, double *gsrc_out,
+                    void *stream);
+/* ref: fluid::ConservedToPrimitiveRegion / ConservedToPrimitiveRobust, src/fluid/fluid.cpp:452-517,
+ * src/fluid/con2prim_robust.hpp:300-453; inclusive index ranges */
+int pb_cons_to_prim(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
+                    const int jb[2], const int kb[2], void *stream);
+/* ref: fixup::ConservedToPrimitiveFixup, src/fixup/fixup_c2p.cpp:44-393 */
+int pb_c2p_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream);
+/* ref: fixup::ApplyFloors, src/fixup/fixup.cpp:286-726. counters (device, 3 x uint64, may be
+ * NULL): [0] floors applied, [1] ceilings applied, [2] in-kernel c2p failures; accumulated. */
+int pb_apply_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons,
+                    unsigned long long *counters, void *stream);
+/* ref: fluid::PrimitiveToConservedRegion, src/fluid/fluid.cpp:368-449 */
+int pb_prim_to_cons(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
+                    const int jb[2], const int kb[2], void *stream);
+/* Ghost fill between blocks of this pack (same GPU). ref: parthenon SendBoundBufs/SetBounds,
+ * external/parthenon/src/bvals/comms/boundary_communication.cpp:49-346. Ships the reference's
+ * FillGhost variable set: cons, plus (bc_prim) prim, temperature, c2p_mu, fail. */
+int pb_halo_exchange_local(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream);
+/* Inter-GPU halos: a "halo plan" is a device int array of nseg segments, 10 ints each:
+ * {block, i0, i1, j0, j1, k0, k1 (inclusive cell ranges), offset_lo, offset_hi (segment start in
+ * the buffer, in zones; 64-bit split in two ints), reserved}. pack gathers the listed zones of
+ * every shipped field into buf; unpack scatters buf into the listed (ghost) zones.
+ * Buffer layout per segment: [field comp][k][j][i]. nvar = pb_halo_nvar(cfg). */
+int pb_halo_nvar(const pb_cfg_t *cfg);
+int pb_halo_pack(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, const int *plan,
+                 int nseg, double *buf, void *stream);
+int pb_halo_unpack(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *plan,
+                   int nseg, const double *buf, void *stream);
+/* Physical boundary ghost fill + Boundaries::ConvertBoundaryConditions,
+ * ref: src/phoebus_boundaries/phoebus_boundaries.cpp:44-448 */
+int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream);
+/* ref: fluid::EstimateTimestepBlock, src/fluid/fluid.cpp:899-944, min over the pack, without
+ * the cfl factor. dt_out: device double, combined with atomic min (caller initialises). */
+int pb_estimate_dt(const pb_pack_t *pack, const pb_cfg_t *cfg, int has_face_speeds, double *dt_out,
+                   void *stream);
+
+/* One Runge-Kutta stage in the order of PhoebusDriver::RungeKuttaStage's fluid sub-graph
+ * (ref: src/phoebus_driver.cpp:204-738) for a single-GPU pack: sources, fluxes, CT, FixFluxes,
+ * update, stale-prim fixup + floors, local halo, BCs, c2p, fixup, floors.
+ * sc0/sc1/base: conserved containers (stage in, stage out, "base"). */
+int pb_rk_stage(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc0, double *base, double *sc1,
+                double beta, double dt, unsigned long long *counters, void *stream);
+/* first half (through the stale-prim floors) and second half (BCs onwards) of pb_rk_stage, for
+ * callers that put an inter-GPU halo exchange in between */
+int pb_rk_stage_pre(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc0, double *base, double *sc1,
+                    double beta, double dt, unsigned long long *counters, void *stream);
+int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1,
+                     unsigned long long *counters, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHOEBUS_B200_H_ */

@@ -1,0 +1,186 @@
+// fluid::CalculateFluxes for a whole pack: fused reconstruction + Riemann solve, one launch per
+// direction (ref: src/fluid/fluid.cpp:659-773, src/fluid/riemann.hpp:256-301).
+//
+// The reference runs two kernels per MeshBlock ("Reconstruct" writes ql/qr for all directions to
+// global memory, "CalculateFluxes" reads them back: 120 words/zone of round trip). Here a CTA owns a
+// tile of stencil pencils: every thread reconstructs the 7/10 primitives of ONE cell (exactly one
+// reconstruction per cell and direction, as in the reference), hands its left-face state to the
+// neighbouring thread through shared memory, keeps its right-face state in registers and then solves
+// the Riemann problem at its own lower face. ql/qr never touch HBM.
+#include "pb_device.cuh"
+#include "pb_host.hpp"
+
+namespace pb {
+
+struct FluxTile {
+  int NS;      // cells along the stencil axis handled per pencil (n + 2)
+  int TT;      // pencils per CTA
+  int nT1, nT; // transverse extents: fast one, total pencils per block
+  int tiles;   // CTAs per block
+};
+
+template <int DIR, int RECON, bool MHD>
+__global__ void flux_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const FluxTile ft) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  extern __shared__ Real s_ql[]; // [NP][(NS+1)*TT]
+  const Lay L(cfg);
+  const int b = blockIdx.x / ft.tiles, tile = blockIdx.x % ft.tiles;
+  const int NS = ft.NS, TT = ft.TT;
+  const int tid = threadIdx.x;
+  int sI, tI;
+  if (DIR == 1) {
+    sI = tid % NS;
+    tI = tid / NS;
+  } else {
+    tI = tid % TT;
+    sI = tid / TT;
+  }
+  const int col = tile * TT + tI;
+  const bool valid = (col < ft.nT) && (sI < NS) && (tI < TT);
+  const int t1 = col % ft.nT1, t2 = col / ft.nT1;
+  int i, j, k, st;
+  if (DIR == 1) {
+    i = L.is - 1 + sI;
+    j = L.js - L.dj + t1;
+    k = L.ks - L.dk + t2;
+    st = 1;
+  } else if (DIR == 2) {
+    i = L.is - 1 + t1;
+    j = L.js - 1 + sI;
+    k = L.ks - L.dk + t2;
+    st = L.ni;
+  } else {
+    i = L.is - 1 + t1;
+    j = L.js - 1 + t2;
+    k = L.ks - 1 + sI;
+    st = L.ni * L.nj;
+  }
+  const int plane = (NS + 1) * TT;
+  const int slot_w = (DIR == 1) ? tI * (NS + 1) + sI + 1 : (sI + 1) * TT + tI; // my ql goes to face s+1
+  const int slot_r = (DIR == 1) ? tI * (NS + 1) + sI : sI * TT + tI;           // face s reads cell s-1's ql
+  const int o = L.idx(k, j, i);
+  Real qR[NP];
+  if (valid) {
+    const Real *v = pack.prim + (size_t)b * NP * L.ncell + o;
+#pragma unroll
+    for (int n = 0; n < NP; ++n) {
+      const Real *p = v + (size_t)n * L.ncell;
+      Real ql;
+      recon5<RECON>(__ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), ql, qR[n]);
+      s_ql[n * plane + slot_w] = ql;
+    }
+  }
+  __syncthreads();
+  if (!valid || sI == 0) return;
+  Real qL[NP];
+#pragma unroll
+  for (int n = 0; n < NP; ++n) qL[n] = s_ql[n * plane + slot_r];
+
+  const pb_block_t &blk = pack.blocks[b];
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  const int gcell = gt.cell(k, j, i);
+  // FaceGeom (ref: riemann.hpp:32-54): only gamma^{dd} of the inverse metric is needed
+  g.alpha = gt.at(DIR, G_ALPHA, gcell);
+  g.detgam = gt.at(DIR, G_DETGAM, gcell);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) g.beta[d] = gt.at(DIR, G_BCON + d, gcell);
+#pragma unroll
+  for (int m = 0; m < 10; ++m) g.gcov[m] = gt.at(DIR, G_GCOV + m, gcell);
+  const Real gdd = gt.at(DIR, G_GAMCON + flat4(DIR - 1, DIR - 1), gcell);
+  const Real gdet = g.alpha * g.detgam; // DetG = alpha * sqrt(gamma), cached_system.hpp:371-374
+  FloorCtx fc;
+  load_floor(pack.floor_tab, blk.floor_slot, L.ni, DIR == 1 ? 1 : 0, i, fc.A, fc.B);
+  fc.x1 = (DIR == 1) ? Xf(blk, 0, i) : Xc(blk, 0, i);
+  fc.x2 = (DIR == 2) ? Xf(blk, 1, j) : Xc(blk, 1, j);
+  fc.x3 = (DIR == 3) ? Xf(blk, 2, k) : Xc(blk, 2, k);
+
+  Real Ul[NCn], Fl[NCn], Ur[NCn], Fr[NCn], vml, vpl, vmr, vpr;
+  prim_to_flux<DIR, MHD>(cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
+  prim_to_flux<DIR, MHD>(cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+  Real *fl = pack.flux + ((size_t)b * L.ndim + (DIR - 1)) * NCn * L.ncell + o;
+  Real speed;
+  if (cfg.riemann == 0) { // llf, ref: riemann.hpp:256-276
+    const Real cmax = dmax(dmax(-vml, vpl), dmax(-vmr, vpr));
+#pragma unroll
+    for (int m = 0; m < NCn; m++)
+      fl[(size_t)m * L.ncell] = 0.5 * ((Fl[m] + Fr[m]) * gdet - cmax * ((Ur[m] - Ul[m]) * g.detgam));
+    speed = cmax;
+  } else { // hll, ref: riemann.hpp:278-301
+    const Real cl = dmin(dmin(vml, vmr), 0.0);
+    const Real cr = dmax(dmax(vpl, vpr), 0.0);
+    const Real crcl = cr * cl;
+    const Real inv_cr_cl = ratio(1.0, cr - cl);
+#pragma unroll
+    for (int m = 0; m < NCn; m++)
+      fl[(size_t)m * L.ncell] = ((cr * Fl[m] - cl * Fr[m]) * gdet + crcl * (Ur[m] - Ul[m]) * g.detgam) * inv_cr_cl;
+    speed = dmax(-cl, cr);
+  }
+  pack.fsig[((size_t)b * L.ndim + (DIR - 1)) * L.ncell + o] = speed;
+}
+
+template <int DIR, int RECON, bool MHD>
+static int launch_dir(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
+  const Lay L(cfg);
+  FluxTile ft;
+  int n1, n2;
+  if (DIR == 1) {
+    ft.NS = cfg.nx[0] + 2;
+    n1 = L.je - L.js + 1 + 2 * L.dj;
+    n2 = L.ke - L.ks + 1 + 2 * L.dk;
+  } else if (DIR == 2) {
+    ft.NS = cfg.nx[1] + 2;
+    n1 = cfg.nx[0] + 2;
+    n2 = L.ke - L.ks + 1 + 2 * L.dk;
+  } else {
+    ft.NS = cfg.nx[2] + 2;
+    n1 = cfg.nx[0] + 2;
+    n2 = cfg.nx[1] + 2;
+  }
+  ft.nT1 = n1;
+  ft.nT = n1 * n2;
+  int target = flux_threads_target();
+  ft.TT = target / ft.NS;
+  if (ft.TT < 1) ft.TT = 1;
+  if (ft.TT > ft.nT) ft.TT = ft.nT;
+  if (ft.NS * ft.TT > 1024) return set_error(PB_EINVAL, "block too large for the flux tile");
+  ft.tiles = (ft.nT + ft.TT - 1) / ft.TT;
+  const int threads = ft.NS * ft.TT;
+  const size_t smem = (size_t)NC<MHD>::nprim * (ft.NS + 1) * ft.TT * sizeof(Real);
+  auto kern = flux_kernel<DIR, RECON, MHD>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "flux smem attribute");
+  }
+  kern<<<(unsigned)(pack.nblocks * ft.tiles), threads, smem, s>>>(pack, cfg, ft);
+  return check_launch("flux_kernel");
+}
+
+template <int RECON, bool MHD> static int launch_all(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
+  int rc = launch_dir<1, RECON, MHD>(pack, cfg, s);
+  if (rc == 0 && cfg.ndim >= 2) rc = launch_dir<2, RECON, MHD>(pack, cfg, s);
+  if (rc == 0 && cfg.ndim >= 3) rc = launch_dir<3, RECON, MHD>(pack, cfg, s);
+  return rc;
+}
+
+template <bool MHD> static int launch_recon(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
+  switch (cfg.recon) {
+  case 0: return launch_all<0, MHD>(pack, cfg, s);
+  case 1: return launch_all<1, MHD>(pack, cfg, s);
+  case 2: return launch_all<2, MHD>(pack, cfg, s);
+  case 3: return launch_all<3, MHD>(pack, cfg, s);
+  }
+  return set_error(PB_EINVAL, "unknown reconstruction");
+}
+
+} // namespace pb
+
+extern "C" int pb_calculate_fluxes(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream) {
+  using namespace pb;
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (cfg->ng < 3 && cfg->recon >= 2) return set_error(PB_EINVAL, "weno5/mp5 need nghost >= 3");
+  if (cfg->riemann != 0 && cfg->riemann != 1) return set_error(PB_EINVAL, "unknown riemann solver");
+  cudaStream_t s = (cudaStream_t)stream;
+  return cfg->mhd ? launch_recon<true>(*pack, *cfg, s) : launch_recon<false>(*pack, *cfg, s);
+}

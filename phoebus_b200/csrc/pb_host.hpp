@@ -1,0 +1,22 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and launch checks.
+#ifndef PB_HOST_HPP_
+#define PB_HOST_HPP_
+
+#include <cuda_runtime.h>
+
+#include "../../include/phoebus_b200.h"
+
+namespace pb {
+
+int set_error(int code, const char *msg);
+int set_cuda_error(cudaError_t e, const char *where);
+// cudaPeekAtLastError after a launch (does not synchronise)
+int check_launch(const char *kernel);
+// common argument validation for tasks
+int check_args(const pb_pack_t *pack, const pb_cfg_t *cfg);
+// tunables (environment overrides, read once): PB_FLUX_THREADS, PB_ZONE_THREADS
+int flux_threads_target();
+int zone_threads();
+
+} // namespace pb
+#endif

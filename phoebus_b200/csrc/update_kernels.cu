@@ -1,0 +1,443 @@
+// FluxCT, FixFluxes, FluxDivergence, CalculateFluidSourceTerms, WeightedSumData and their fusion
+// (divergence + geometric sources + RK update in one pass over the interior zones of a pack).
+#include "pb_device.cuh"
+#include "pb_host.hpp"
+
+namespace pb {
+
+PB_DEV bool interior_zone(const Lay &L, int nblocks, int ei, int ej, int ek, int &b, int &k, int &j, int &i) {
+  // zones [is, ie+ei] x [js, je+ej] x [ks, ke+ek]
+  const int ni = L.ie - L.is + 1 + ei, nj = L.je - L.js + 1 + ej, nk = L.ke - L.ks + 1 + ek;
+  const long long nreg = (long long)ni * nj * nk;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nreg * nblocks) return false;
+  b = (int)(t / nreg);
+  int rem = (int)(t % nreg);
+  i = L.is + rem % ni;
+  rem /= ni;
+  j = L.js + rem % nj;
+  k = L.ks + rem / nj;
+  return true;
+}
+
+// ------------------------------------------------------------------ FluxCT
+// ref: src/fluid/fluid.cpp:775-841 (Toth flux-CT). Two launches: the B-flux update reads EMFs of
+// neighbouring corners, and it overwrites the fluxes the EMFs are built from.
+template <int NDIM> __global__ void emf_kernel(const pb_pack_t pack, const pb_cfg_t cfg) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!interior_zone(L, pack.nblocks, 1, 1, NDIM == 3 ? 1 : 0, b, k, j, i)) return;
+  constexpr int NCn = 8;
+  const int N = L.ncell, o = L.idx(k, j, i);
+  const int sj = L.ni, sk = L.ni * L.nj;
+  const Real *fb = pack.flux + (size_t)b * L.ndim * NCn * N;
+  auto F = [&](int dir, int bc) { return fb + ((size_t)(dir - 1) * NCn + CB + bc) * N + o; };
+  Real *emf = pack.emf + (size_t)b * 3 * N + o;
+  if (NDIM == 2) {
+    emf[0] = 0.25 * (F(1, 1)[0] + F(1, 1)[-sj] - F(2, 0)[0] - F(2, 0)[-1]);
+  } else {
+    emf[0] = 0.25 * (F(2, 2)[0] + F(2, 2)[-sk] - F(3, 1)[0] - F(3, 1)[-sj]);
+    emf[(size_t)N] = -0.25 * (F(1, 2)[0] + F(1, 2)[-sk] - F(3, 0)[0] - F(3, 0)[-1]);
+    emf[(size_t)2 * N] = 0.25 * (F(1, 1)[0] + F(1, 1)[-sj] - F(2, 0)[0] - F(2, 0)[-1]);
+  }
+}
+template <int NDIM> __global__ void ct_flux_kernel(const pb_pack_t pack, const pb_cfg_t cfg) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!interior_zone(L, pack.nblocks, 1, 1, NDIM == 3 ? 1 : 0, b, k, j, i)) return;
+  constexpr int NCn = 8;
+  const int N = L.ncell, o = L.idx(k, j, i);
+  const int sj = L.ni, sk = L.ni * L.nj;
+  Real *fb = pack.flux + (size_t)b * L.ndim * NCn * N;
+  auto F = [&](int dir, int bc) -> Real & { return fb[((size_t)(dir - 1) * NCn + CB + bc) * N + o]; };
+  const Real *emf = pack.emf + (size_t)b * 3 * N + o;
+  if (NDIM == 2) {
+    F(1, 0) = 0.0;
+    F(1, 1) = 0.5 * (emf[0] + emf[sj]);
+    F(2, 0) = -0.5 * (emf[0] + emf[1]);
+    F(2, 1) = 0.0;
+  } else {
+    const Real *e0 = emf, *e1 = emf + (size_t)N, *e2 = emf + (size_t)2 * N;
+    F(1, 0) = 0.0;
+    F(1, 1) = 0.5 * (e2[0] + e2[sj]);
+    F(1, 2) = -0.5 * (e1[0] + e1[sk]);
+    F(2, 0) = -0.5 * (e2[0] + e2[1]);
+    F(2, 1) = 0.0;
+    F(2, 2) = 0.5 * (e0[0] + e0[sk]);
+    F(3, 0) = 0.5 * (e1[0] + e1[1]);
+    F(3, 1) = -0.5 * (e0[0] + e0[sj]);
+    F(3, 2) = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------ FixFluxes
+// ref: src/fixup/fixup.cpp:728-1078 (fluid variables). One thread per boundary-face zone; the six
+// faces touch disjoint flux entries except polar's B2 mirror, which only reads the face plane its own
+// thread column owns.
+template <bool MHD> __global__ void fix_fluxes_kernel(const pb_pack_t pack, const pb_cfg_t cfg, int nface_max) {
+  constexpr int NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_block = (long long)2 * L.ndim * nface_max;
+  if (t >= per_block * pack.nblocks) return;
+  const int b = (int)(t / per_block);
+  int rem = (int)(t % per_block);
+  const int f = rem / nface_max; // face id 0..2*ndim-1
+  const int c = rem % nface_max;
+  const pb_block_t &blk = pack.blocks[b];
+  const int bc = blk.bc[f];
+  if (bc <= 0) return;
+  const int dir = f / 2, side = f % 2;
+  const int n1 = L.ie - L.is + 1, n2 = L.je - L.js + 1, n3 = L.ke - L.ks + 1;
+  int i, j, k;
+  if (dir == 0) {
+    if (c >= n2 * n3) return;
+    i = side == 0 ? L.is : L.ie + 1;
+    j = L.js + c % n2;
+    k = L.ks + c / n2;
+  } else if (dir == 1) {
+    if (c >= n1 * n3) return;
+    j = side == 0 ? L.js : L.je + 1;
+    i = L.is + c % n1;
+    k = L.ks + c / n1;
+  } else {
+    if (c >= n1 * n2) return;
+    k = side == 0 ? L.ks : L.ke + 1;
+    i = L.is + c % n1;
+    j = L.js + c / n1;
+  }
+  const int N = L.ncell, o = L.idx(k, j, i);
+  Real *fb = pack.flux + (size_t)b * L.ndim * NCn * N;
+  auto F = [&](int d, int m, int off) -> Real & { return fb[((size_t)(d - 1) * NCn + m) * N + o + off]; };
+  const int d1 = dir + 1;
+  if (dir != 1) { // X1 and X3 faces: outflow / reflect only
+    if (bc == PB_BC_OUTFLOW) {
+      F(d1, CRHO, 0) = side == 0 ? dmin(F(d1, CRHO, 0), 0.0) : dmax(F(d1, CRHO, 0), 0.0);
+    } else if (bc == PB_BC_REFLECT) {
+      F(d1, CRHO, 0) = 0.0;
+      F(d1, CENG, 0) = 0.0;
+    }
+    return;
+  }
+  if (bc == PB_BC_OUTFLOW) {
+    F(2, CRHO, 0) = side == 0 ? dmin(F(2, CRHO, 0), 0.0) : dmax(F(2, CRHO, 0), 0.0);
+  } else if (bc == PB_BC_POLAR) {
+    F(2, CRHO, 0) = 0.0;
+    F(2, CENG, 0) = 0.0;
+    for (int ii = 0; ii < 3; ++ii) {
+      F(2, CMOM + ii, 0) = 0.0;
+      if (MHD) F(2, CB + ii, 0) = 0.0;
+    }
+    if (MHD) {
+      const int sj = L.ni;
+      if (side == 0) {
+        F(1, CB + 1, -sj) = -F(1, CB + 1, 0);
+        if (L.ndim == 3) F(3, CB + 1, -sj) = -F(3, CB + 1, 0);
+      } else {
+        F(1, CB + 1, 0) = -F(1, CB + 1, -sj);
+        if (L.ndim == 3) F(3, CB + 1, 0) = -F(3, CB + 1, -sj);
+      }
+    }
+  } else if (bc == PB_BC_REFLECT) {
+    F(2, CRHO, 0) = 0.0;
+    F(2, CENG, 0) = 0.0;
+    F(2, CMOM + 0, 0) = 0.0;
+    F(2, CMOM + 2, 0) = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------ divergence / sources
+// ref: external/parthenon/src/interface/update.hpp:43-58 (FluxDivHelper)
+template <int NCn> PB_DEV void flux_div(const Lay &L, const pb_block_t &blk, const Real *fb, int o, Real *du) {
+  // uniform_cartesian.hpp:30-40: face areas and the cell volume are products of dx
+  const Real area[3] = {blk.dx[1] * blk.dx[2], blk.dx[0] * blk.dx[2], blk.dx[0] * blk.dx[1]};
+  const Real vol = blk.dx[0] * blk.dx[1] * blk.dx[2];
+  const int st[3] = {1, L.ni, L.ni * L.nj};
+  const int N = L.ncell;
+#pragma unroll
+  for (int l = 0; l < NCn; ++l) {
+    Real acc = 0;
+    for (int d = 0; d < L.ndim; ++d) {
+      const Real *f = fb + ((size_t)d * NCn + l) * N + o;
+      const Real t = (area[d] * __ldg(f + st[d]) - area[d] * __ldg(f));
+      acc = (d == 0) ? t : acc + t;
+    }
+    du[l] = -acc / vol;
+  }
+}
+
+// ref: src/fluid/fluid.cpp:593-654 with src/fluid/tmunu.hpp:63-131 and
+// src/geometry/geometry_utils.hpp:73-80 (connection from metric derivatives); src[4] = S1,S2,S3,tau
+template <bool MHD>
+PB_DEV void source_zone(const GeomTab &gt, int gcell, const Real *prim, int N, Real src[4]) {
+  constexpr int prs = NC<MHD>::prs;
+  PointGeom g;
+  g.load(gt, 0, gcell);
+  // --- Tmunu (contravariant)
+  Real vp[3] = {prim[(size_t)PVEL * N], prim[(size_t)(PVEL + 1) * N], prim[(size_t)(PVEL + 2) * N]};
+  Real B[3] = {0, 0, 0};
+  if (MHD)
+    for (int a = 0; a < 3; ++a) B[a] = prim[(size_t)(PB_ + a) * N];
+  const Real W = lorentz_factor(vp, g); // gamma_ij is the spatial block of g_mu_nu
+  Real Bdotv = 0.0, Bsq = 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 3; ++bb) {
+      Bdotv += B[a] * (vp[bb] / W) * g.g4(a + 1, bb + 1);
+      Bsq += B[a] * B[bb] * g.g4(a + 1, bb + 1);
+    }
+  const Real iW = ratio(1., W);
+  const Real alpha = g.alpha;
+  Real u[4], bv[4];
+  u[0] = ratio(W, fabs(alpha));
+  bv[0] = u[0] * Bdotv;
+#pragma unroll
+  for (int l = 1; l < 4; ++l) {
+    u[l] = vp[l - 1] - u[0] * g.beta[l - 1];
+    bv[l] = iW * (B[l - 1] + alpha * bv[0] * u[l]);
+  }
+  const Real bsq = Bsq * iW * iW + Bdotv * Bdotv;
+  // SpacetimeMetricInverse, ref: cached_system.hpp:330-349
+  Real gg[4][4];
+  {
+    Real alpha2 = alpha;
+    alpha2 *= alpha2;
+    gg[0][0] = -ratio(1, alpha2);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) gg[m + 1][0] = gg[0][m + 1] = ratio(g.beta[m], alpha2);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        gg[m + 1][n + 1] = g.gc3(m, n);
+        gg[m + 1][n + 1] -= gg[0][m + 1] * gg[0][n + 1] * alpha2;
+      }
+  }
+  const Real rho = prim[(size_t)PRHO * N], uu = prim[(size_t)PENG * N], P = prim[(size_t)prs * N];
+  const Real A = rho + uu + P + bsq;
+  const Real Bc = P + 0.5 * bsq;
+  Real T[4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) T[m][n] = A * u[m] * u[n] + Bc * gg[m][n] - bv[m] * bv[n];
+  // --- metric derivatives and connection
+  const Real gdet = alpha * g.detgam;
+  Real dg[4][4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      dg[m][n][0] = 0.0;
+#pragma unroll
+      for (int s = 1; s < 4; ++s) dg[m][n][s] = gt.der(G_DG + 3 * flat4(m, n) + (s - 1), gcell);
+    }
+  Real gam[4][4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) gam[a][b][c] = 0.5 * (dg[b][a][c] + dg[c][a][b] - dg[b][c][a]);
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    Real src_mom = 0.0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) src_mom += T[m][n] * (dg[n][l + 1][m] - gam[l + 1][n][m]);
+    src[l] = gdet * src_mom;
+  }
+  Real TGam = 0.0;
+  const Real inv_alpha2 = ratio(1, alpha * alpha);
+  const Real gcon0[4] = {-inv_alpha2, inv_alpha2 * g.beta[0], inv_alpha2 * g.beta[1], inv_alpha2 * g.beta[2]};
+#pragma unroll
+  for (int m = 0; m < 4; m++)
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+      Real gam0 = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) gam0 += gcon0[r] * gam[r][m][n];
+      TGam += T[m][n] * gam0;
+    }
+  Real Ta = 0.0;
+  Real da[4] = {0.0, gt.der(G_DALPHA + 0, gcell), gt.der(G_DALPHA + 1, gcell), gt.der(G_DALPHA + 2, gcell)};
+#pragma unroll
+  for (int m = 0; m < 4; m++) Ta += T[m][0] * da[m];
+  src[3] = gdet * alpha * (Ta - TGam);
+}
+
+template <bool MHD> __global__ void divergence_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *dudt) {
+  constexpr int NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!interior_zone(L, pack.nblocks, 0, 0, 0, b, k, j, i)) return;
+  const int N = L.ncell, o = L.idx(k, j, i);
+  Real du[NCn];
+  flux_div<NCn>(L, pack.blocks[b], pack.flux + (size_t)b * L.ndim * NCn * N, o, du);
+#pragma unroll
+  for (int l = 0; l < NCn; ++l) dudt[((size_t)b * NCn + l) * N + o] = du[l];
+}
+
+template <bool MHD> __global__ void source_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *gsrc) {
+  constexpr int NP = NC<MHD>::nprim;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!interior_zone(L, pack.nblocks, 0, 0, 0, b, k, j, i)) return;
+  const int N = L.ncell, o = L.idx(k, j, i);
+  const GeomTab gt(cfg, pack.geom, pack.blocks[b].geom_slot);
+  Real src[4];
+  source_zone<MHD>(gt, gt.cell(k, j, i), pack.prim + (size_t)b * NP * N + o, N, src);
+#pragma unroll
+  for (int l = 0; l < 4; ++l) gsrc[((size_t)b * 4 + l) * N + o] = src[l];
+}
+
+// Fused: dudt = -div F; dudt[S,tau] = 1*dudt + 1*gsrc (SumData); u_avg = beta*u0 + (1-beta)*ubase
+// (AverageIndependentData); uout = 1*u_avg + bdt*dudt (UpdateIndependentData).
+// ref: src/phoebus_driver.cpp:560-576, external/parthenon/src/interface/update.hpp:71-136
+template <bool MHD>
+__global__ void update_fused_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *u0, const Real *ubase,
+                                    Real beta, Real bdt, Real *uout, Real *dudt_out, Real *gsrc_out) {
+  constexpr int NCn = NC<MHD>::ncons, NP = NC<MHD>::nprim;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!interior_zone(L, pack.nblocks, 0, 0, 0, b, k, j, i)) return;
+  const int N = L.ncell, o = L.idx(k, j, i);
+  Real du[NCn];
+  flux_div<NCn>(L, pack.blocks[b], pack.flux + (size_t)b * L.ndim * NCn * N, o, du);
+  const GeomTab gt(cfg, pack.geom, pack.blocks[b].geom_slot);
+  Real src[4];
+  source_zone<MHD>(gt, gt.cell(k, j, i), pack.prim + (size_t)b * NP * N + o, N, src);
+  if (gsrc_out) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) gsrc_out[((size_t)b * 4 + l) * N + o] = src[l];
+  }
+#pragma unroll
+  for (int l = 0; l < 4; ++l) du[CMOM + l] = 1.0 * du[CMOM + l] + 1.0 * src[l];
+  const Real w2 = 1.0 - beta;
+#pragma unroll
+  for (int l = 0; l < NCn; ++l) {
+    const size_t a = ((size_t)b * NCn + l) * N + o;
+    const Real uavg = beta * u0[a] + w2 * ubase[a];
+    uout[a] = 1.0 * uavg + bdt * du[l];
+    if (dudt_out) dudt_out[a] = du[l];
+  }
+}
+
+// Ghost zones of the same update: WeightedSumData runs over ENTIRE arrays (update.hpp:77-80) and
+// dUdt is zero outside the interior, so uout = beta*u0 + (1-beta)*ubase there. The values matter
+// only to the stale-prim ApplyFloors of region 7 (which may re-invert a ghost zone and thereby
+// advance its c2p_mu history) and are overwritten by the halo exchange / BCs afterwards.
+__global__ void update_ghost_kernel(const pb_cfg_t cfg, int nblocks, int ncons, const Real *u0, const Real *ubase,
+                                    Real beta, Real *uout) {
+  const Lay L(cfg);
+  const int N = L.ncell;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * nblocks) return;
+  const int b = (int)(t / N), o = (int)(t % N);
+  const int i = o % L.ni, j = (o / L.ni) % L.nj, k = o / (L.ni * L.nj);
+  if (i >= L.is && i <= L.ie && j >= L.js && j <= L.je && k >= L.ks && k <= L.ke) return;
+  const Real w2 = 1.0 - beta;
+  for (int l = 0; l < ncons; ++l) {
+    const size_t a = ((size_t)b * ncons + l) * N + o;
+    const Real uavg = beta * u0[a] + w2 * ubase[a];
+    uout[a] = 1.0 * uavg + 0.0;
+  }
+}
+
+__global__ void weighted_sum_kernel(const Real *x, const Real *y, Real w1, Real w2, Real *z, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) z[t] = w1 * x[t] + w2 * y[t];
+}
+
+static unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+} // namespace pb
+
+using namespace pb;
+
+extern "C" int pb_flux_ct(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cfg->mhd || cfg->ndim == 1) return PB_OK; // ref: fluid.cpp:776-781
+  const Lay L(*cfg);
+  const long long n = (long long)(cfg->nx[0] + 1) * (cfg->nx[1] + 1) * (cfg->ndim == 3 ? cfg->nx[2] + 1 : 1) * pack->nblocks;
+  const int T = 256;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->ndim == 2) {
+    emf_kernel<2><<<grid_for(n, T), T, 0, s>>>(*pack, *cfg);
+    ct_flux_kernel<2><<<grid_for(n, T), T, 0, s>>>(*pack, *cfg);
+  } else {
+    emf_kernel<3><<<grid_for(n, T), T, 0, s>>>(*pack, *cfg);
+    ct_flux_kernel<3><<<grid_for(n, T), T, 0, s>>>(*pack, *cfg);
+  }
+  return check_launch("flux_ct");
+}
+
+extern "C" int pb_fix_fluxes(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cfg->enable_flux_fixup) return PB_OK; // ref: fixup.cpp:734-736
+  const int n1 = cfg->nx[0], n2 = cfg->ndim >= 2 ? cfg->nx[1] : 1, n3 = cfg->ndim >= 3 ? cfg->nx[2] : 1;
+  int nface_max = n2 * n3;
+  if (n1 * n3 > nface_max) nface_max = n1 * n3;
+  if (n1 * n2 > nface_max) nface_max = n1 * n2;
+  const long long n = (long long)2 * cfg->ndim * nface_max * pack->nblocks;
+  const int T = 128;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) fix_fluxes_kernel<true><<<grid_for(n, T), T, 0, s>>>(*pack, *cfg, nface_max);
+  else fix_fluxes_kernel<false><<<grid_for(n, T), T, 0, s>>>(*pack, *cfg, nface_max);
+  return check_launch("fix_fluxes_kernel");
+}
+
+static long long n_interior(const pb_pack_t *pack, const pb_cfg_t *cfg) {
+  return (long long)cfg->nx[0] * (cfg->ndim >= 2 ? cfg->nx[1] : 1) * (cfg->ndim >= 3 ? cfg->nx[2] : 1) * pack->nblocks;
+}
+
+extern "C" int pb_flux_divergence(const pb_pack_t *pack, const pb_cfg_t *cfg, double *dudt, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  const int T = 256;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) divergence_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, dudt);
+  else divergence_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, dudt);
+  return check_launch("divergence_kernel");
+}
+
+extern "C" int pb_source_terms(const pb_pack_t *pack, const pb_cfg_t *cfg, double *gsrc, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  const int T = zone_threads();
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) source_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, gsrc);
+  else source_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, gsrc);
+  return check_launch("source_kernel");
+}
+
+extern "C" int pb_weighted_sum(const double *x, const double *y, double w1, double w2, double *z, long long n,
+                               void *stream) {
+  if (n <= 0) return PB_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  weighted_sum_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, w1, w2, z, n);
+  return check_launch("weighted_sum_kernel");
+}
+
+extern "C" int pb_update_fused(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *u0, const double *ubase,
+                               double beta, double bdt, double *uout, double *dudt_out, double *gsrc_out,
+                               void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!u0 || !ubase || !uout) return set_error(PB_EINVAL, "NULL conserved container");
+  const int T = zone_threads();
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd)
+    update_fused_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, dudt_out, gsrc_out);
+  else
+    update_fused_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, dudt_out, gsrc_out);
+  const Lay L(*cfg);
+  const long long ntot = (long long)L.ncell * pack->nblocks;
+  update_ghost_kernel<<<grid_for(ntot, 256), 256, 0, s>>>(*cfg, pack->nblocks, 5 + 3 * cfg->mhd, u0, ubase, beta, uout);
+  return check_launch("update_fused_kernel");
+}

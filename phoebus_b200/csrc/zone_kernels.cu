@@ -1,0 +1,611 @@
+// One-zone-per-thread tasks over a whole pack: ConservedToPrimitive (robust), its failure fixup,
+// ApplyFloors, PrimitiveToConserved, physical boundary conditions, the CFL estimate.
+#include "pb_device.cuh"
+#include "pb_host.hpp"
+
+namespace pb {
+
+// ------------------------------------------------------------------ helpers
+struct Region {
+  int i0, i1, j0, j1, k0, k1;
+  __host__ __device__ int ni() const { return i1 - i0 + 1; }
+  __host__ __device__ int nj() const { return j1 - j0 + 1; }
+  __host__ __device__ int nk() const { return k1 - k0 + 1; }
+  __host__ __device__ long long n() const { return (long long)ni() * nj() * nk(); }
+};
+
+PB_DEV bool zone_of_thread(const Region &r, int nblocks, int &b, int &k, int &j, int &i) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nreg = r.n();
+  if (t >= nreg * nblocks) return false;
+  b = (int)(t / nreg);
+  int rem = (int)(t % nreg);
+  i = r.i0 + rem % r.ni();
+  rem /= r.ni();
+  j = r.j0 + rem % r.nj();
+  k = r.k0 + rem / r.nj();
+  return true;
+}
+
+PB_DEV FloorCtx cell_floor_ctx(const pb_pack_t &pack, const pb_block_t &blk, const Lay &L, int k, int j, int i) {
+  FloorCtx fc;
+  load_floor(pack.floor_tab, blk.floor_slot, L.ni, 0, i, fc.A, fc.B);
+  fc.x1 = Xc(blk, 0, i);
+  fc.x2 = Xc(blk, 1, j);
+  fc.x3 = Xc(blk, 2, k);
+  return fc;
+}
+
+template <int N> PB_DEV void load_comps(const Real *base, int ncell, Real *out) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) out[n] = base[(size_t)n * ncell];
+}
+template <int N> PB_DEV void store_comps(Real *base, int ncell, const Real *in) {
+#pragma unroll
+  for (int n = 0; n < N; ++n) base[(size_t)n * ncell] = in[n];
+}
+
+// Field pointers of one zone
+template <bool MHD> struct ZonePtr {
+  Real *cons, *prim, *temp, *mu, *fail, *csig;
+  int ncell;
+  PB_DEV ZonePtr(const pb_pack_t &pack, Real *cons_slab, const Lay &L, int b, int o) : ncell(L.ncell) {
+    cons = cons_slab + (size_t)b * NC<MHD>::ncons * L.ncell + o;
+    prim = pack.prim + (size_t)b * NC<MHD>::nprim * L.ncell + o;
+    temp = pack.temp + (size_t)b * L.ncell + o;
+    mu = pack.c2p_mu + (size_t)b * L.ncell + o;
+    fail = pack.fail + (size_t)b * L.ncell + o;
+    csig = pack.csig + (size_t)b * L.ndim * L.ncell + o;
+  }
+};
+
+// c2p on one zone with the reference's write pattern: nothing is written when the NaN guard trips,
+// only p.bfield when the root is not bracketed (the reference aborts there; we count it).
+template <bool MHD>
+PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const ZonePtr<MHD> &z, int ndim,
+                            Real *U, Real *P, unsigned long long *err_count) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  Real temp, sig[3];
+  Real mu = *z.mu;
+  const Real D0 = U[CRHO], S0 = U[CMOM], S1 = U[CMOM + 1], S2 = U[CMOM + 2], T0 = U[CENG];
+  bool unbracketed;
+  const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
+  const bool ok = c2p_zone<MHD>(cfg, fc, g, U, P, temp, mu, sig, unbracketed);
+  if (nan_in) return false;
+  if (unbracketed) {
+    if (MHD) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) z.prim[(size_t)(PB_ + a) * z.ncell] = P[PB_ + a];
+    }
+    if (err_count) atomicAdd(err_count, 1ULL);
+    return false;
+  }
+  store_comps<NP>(z.prim, z.ncell, P);
+  *z.temp = temp;
+  *z.mu = mu;
+  for (int a = 0; a < ndim; ++a) z.csig[(size_t)a * z.ncell] = sig[a];
+  if (U[CRHO] != D0 || U[CMOM] != S0 || U[CMOM + 1] != S1 || U[CMOM + 2] != S2 || U[CENG] != T0 ||
+      isnan(U[CRHO]) || isnan(U[CMOM]) || isnan(U[CMOM + 1]) || isnan(U[CMOM + 2]) || isnan(U[CENG])) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * z.ncell] = U[n];
+  }
+  (void)NCn;
+  return ok;
+}
+
+// ------------------------------------------------------------------ ConToPrim::Solve
+// ref: src/fluid/fluid.cpp:477-517
+template <bool MHD>
+__global__ void c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                           unsigned long long *err_count) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  const pb_block_t &blk = pack.blocks[b];
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  Real U[NCn], P[NP];
+  load_comps<NCn>(z.cons, L.ncell, U);
+  const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, L.ndim, U, P, err_count);
+  *z.fail = ok ? 1.0 : 0.0;
+}
+
+// ------------------------------------------------------------------ ConToPrim::Solve fixup
+// ref: src/fixup/fixup_c2p.cpp:170-353
+template <bool MHD>
+__global__ void c2p_fixup_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg) {
+  constexpr int NP = NC<MHD>::nprim, prs = NC<MHD>::prs, gm1 = NC<MHD>::gm1;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  if (*z.fail != 0.0) return;
+  const int N = L.ncell;
+  const int st1 = L.ni, st2 = L.ni * L.nj;
+  const Real *fl = z.fail;
+  const Eos eos(cfg);
+  const Real gamma_max = cfg.gam_max;
+  auto fixup = [&](int iv, Real inv_mask_sum) {
+    Real *v = z.prim + (size_t)iv * N;
+    Real acc = fl[-1] * v[-1] + fl[1] * v[1];
+    if (L.ndim > 1) {
+      acc += fl[-st1] * v[-st1] + fl[st1] * v[st1];
+      if (L.ndim == 3) acc += fl[-st2] * v[-st2] + fl[st2] * v[st2];
+    }
+    return inv_mask_sum * acc;
+  };
+  Real num_valid = fl[-1] + fl[1];
+  if (L.ndim > 1) num_valid += fl[-st1] + fl[st1];
+  if (L.ndim == 3) num_valid += fl[-st2] + fl[st2];
+  Real P[NP];
+  load_comps<NP>(z.prim, N, P);
+  if (num_valid > 0.5 && cfg.c2p_failure_strategy == 0) {
+    const Real norm = 1.0 / num_valid;
+    P[PRHO] = fixup(PRHO, norm);
+    for (int pv = PVEL; pv <= PVEL + 2; pv++) P[pv] = fixup(pv, norm);
+    P[PENG] = fixup(PENG, norm);
+    P[PRHO] = dmax(P[PRHO], 100. * R_SMALL);
+    P[PENG] = dmax(P[PENG], 100. * R_SMALL);
+  } else {
+    P[PRHO] = 100. * R_SMALL;
+    P[PENG] = 100. * R_SMALL;
+    for (int ii = 0; ii < 3; ++ii) P[PVEL + ii] = 0.;
+  }
+  const pb_block_t &blk = pack.blocks[b];
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  Real vpcon[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
+  Real W = lorentz_factor(vpcon, g);
+  if (W > gamma_max) {
+    const Real rescale = sqrt(gamma_max * gamma_max - 1.) / (W * W - 1.); // sic, ref: fixup_c2p.cpp:271
+    for (int ii = 0; ii < 3; ++ii) vpcon[ii] *= rescale;
+    for (int ii = 0; ii < 3; ++ii) P[PVEL + ii] = vpcon[ii];
+    W = gamma_max;
+  }
+  const Real temp = eos.T_rho_sie(P[PRHO], ratio(P[PENG], P[PRHO]));
+  P[prs] = eos.P_rho_T(P[PRHO], temp);
+  P[gm1] = ratio(eos.K_rho_T(P[PRHO], temp), P[prs]);
+  Real S[3], bcons[3], bp[3] = {0.0, 0.0, 0.0}, sig[3], D, tau;
+  if (MHD)
+    for (int a = 0; a < 3; ++a) bp[a] = P[PB_ + a];
+  p2c<true>(P[PRHO], vpcon, bp, P[PENG], P[prs], P[gm1], g, D, S, bcons, tau, sig);
+  store_comps<NP>(z.prim, N, P);
+  *z.temp = temp;
+  z.cons[(size_t)CRHO * N] = D;
+  for (int a = 0; a < 3; ++a) z.cons[(size_t)(CMOM + a) * N] = S[a];
+  z.cons[(size_t)CENG * N] = tau;
+  for (int a = 0; a < L.ndim; ++a) z.csig[(size_t)a * N] = sig[a];
+}
+
+// ------------------------------------------------------------------ ApplyFloors
+// ref: src/fixup/fixup.cpp:370-684 (fluid part)
+template <bool MHD>
+__global__ void floors_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                              unsigned long long *counters) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons, prs = NC<MHD>::prs, gm1 = NC<MHD>::gm1;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  const int N = L.ncell;
+  const pb_block_t &blk = pack.blocks[b];
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  const Eos eos(cfg);
+  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+  Real rho_floor = 0.0, sie_floor; // ref passes an uninitialised rho_floor; only ExpX1RhoU reads it
+  get_floors(cfg, fc.A, fc.B, fc.x1, fc.x2, fc.x3, rho_floor, sie_floor);
+  const Real gamma_max = cfg.gam_max, e_max = cfg.sie_max;
+  const Real bsqorho_max = cfg.bsqorho_max, bsqou_max = cfg.bsqou_max;
+  Real rho_floor_max = rho_floor;
+  Real u_floor_max = rho_floor * sie_floor;
+  bool floor_applied = false, ceiling_applied = false;
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  const Real alpha = g.alpha;
+  Real P[NP];
+  load_comps<NP>(z.prim, N, P);
+  Real bp[3] = {0, 0, 0};
+  if (MHD)
+    for (int a = 0; a < 3; ++a) bp[a] = P[PB_ + a];
+  if (cfg.enable_mhd_floors) {
+    Real Bsq = 0.0, Bdotv = 0.0;
+    const Real vp[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
+    const Real W = lorentz_factor(vp, g);
+    const Real iW = 1.0 / W;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        Bsq += g.g4(a + 1, c + 1) * bp[a] * bp[c];
+        Bdotv += g.g4(a + 1, c + 1) * bp[a] * vp[c]; // vp, not vp/W: ref fixup.cpp:420-425
+      }
+    const Real bcon0 = W * Bdotv / alpha;
+    const Real bsq = (Bsq + alpha * alpha * bcon0 * bcon0) * iW * iW;
+    rho_floor_max = dmax(rho_floor_max, bsq / bsqorho_max);
+    u_floor_max = dmax(u_floor_max, bsq / bsqou_max);
+    rho_floor_max = dmax(rho_floor_max, dmax(P[PENG], u_floor_max) / e_max);
+  }
+  Real drho = rho_floor_max - P[PRHO];
+  Real du = u_floor_max - P[PENG];
+  if (drho > 0. || du > 0.) {
+    floor_applied = true;
+    drho = dmax(drho, du / sie_floor);
+    du = dmax(du, sie_floor * drho);
+  }
+  Real U[NCn];
+  bool have_U = false, store_P = false, store_U = false;
+  Real temp_out = 0.0;
+  if (floor_applied) {
+    if (counters) atomicAdd(&counters[0], 1ULL);
+    load_comps<NCn>(z.cons, N, U);
+    have_U = true;
+    const Real vp_normalobs[3] = {0, 0, 0};
+    const Real dprs = eos.P_rho_sie(drho, ratio(du, drho));
+    const Real dgm1 = ratio(eos.K_rho_sie(drho, ratio(du, drho)), dprs);
+    Real dcrho, dS[3], dBcons[3], dtau, nosig[3];
+    p2c<false>(drho, vp_normalobs, bp, du, dprs, dgm1, g, dcrho, dS, dBcons, dtau, nosig);
+    U[CRHO] += dcrho;
+    for (int a = 0; a < 3; ++a) U[CMOM + a] += dS[a];
+    U[CENG] += dtau;
+    // the in-kernel c2p reads the updated cons and writes prims/temp/mu/csig/cons itself
+#pragma unroll
+    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * N] = U[n];
+    Real Pn[NP];
+    load_comps<NP>(z.prim, N, Pn);
+    const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
+    const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, L.ndim, U, Pn, nullptr);
+    // refresh the local view of the zone from what c2p wrote
+    load_comps<NP>(z.prim, N, P);
+    load_comps<NCn>(z.cons, N, U);
+    (void)nan_in;
+    if (!ok) {
+      if (counters) atomicAdd(&counters[2], 1ULL);
+      P[PRHO] = drho;
+      for (int a = 0; a < 3; ++a) P[PVEL + a] = vp_normalobs[a];
+      P[PENG] = du;
+      temp_out = eos.T_rho_sie(P[PRHO], P[PENG] / P[PRHO]);
+      *z.temp = temp_out;
+      p2c<false>(drho, vp_normalobs, bp, du, dprs, dgm1, g, U[CRHO], dS, dBcons, U[CENG], nosig);
+      for (int a = 0; a < 3; ++a) U[CMOM + a] = dS[a];
+      store_P = store_U = true;
+    }
+    // bp keeps the pre-c2p p.bfield, as in the reference (fixup.cpp:441-447)
+  }
+  Real vpcon[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
+  const Real W = lorentz_factor(vpcon, g);
+  if (W > gamma_max || P[PENG] / P[PRHO] > e_max) ceiling_applied = true;
+  if (ceiling_applied) {
+    if (counters) atomicAdd(&counters[1], 1ULL);
+    if (!have_U) {
+      load_comps<NCn>(z.cons, N, U);
+      have_U = true;
+    }
+    const Real rescale = sqrt(gamma_max * gamma_max - 1.) / (W * W - 1.); // sic, ref: fixup.cpp:510
+    for (int a = 0; a < 3; ++a) vpcon[a] *= rescale;
+    for (int a = 0; a < 3; ++a) P[PVEL + a] = vpcon[a];
+    Real dS[3], dBcons[3], nosig[3];
+    p2c<false>(P[PRHO], vpcon, bp, P[PENG], P[prs], P[gm1], g, U[CRHO], dS, dBcons, U[CENG], nosig);
+    for (int a = 0; a < 3; ++a) U[CMOM + a] = dS[a];
+    store_P = store_U = true;
+  }
+  if (floor_applied || ceiling_applied) {
+    temp_out = eos.T_rho_sie(P[PRHO], ratio(P[PENG], P[PRHO]));
+    P[prs] = eos.P_rho_T(P[PRHO], temp_out);
+    P[gm1] = ratio(eos.K_rho_T(P[PRHO], temp_out), P[prs]);
+    *z.temp = temp_out;
+    store_P = true;
+  }
+  if (store_P) store_comps<NP>(z.prim, N, P);
+  if (store_U) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * N] = U[n];
+  }
+}
+
+// ------------------------------------------------------------------ PrimToCons
+// ref: src/fluid/fluid.cpp:368-449
+template <bool MHD>
+PB_DEV void p2c_zone_global(const pb_cfg_t &cfg, const PointGeom &g, const ZonePtr<MHD> &z, int ndim) {
+  constexpr int NP = NC<MHD>::nprim, prs = NC<MHD>::prs, gm1 = NC<MHD>::gm1;
+  const int N = z.ncell;
+  Real P[NP];
+  load_comps<NP>(z.prim, N, P);
+  Real S[3], bcons[3], sig[3], bp[3] = {0, 0, 0}, D, tau;
+  const Real vel[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
+  if (MHD)
+    for (int a = 0; a < 3; ++a) bp[a] = P[PB_ + a];
+  p2c<true>(P[PRHO], vel, bp, P[PENG], P[prs], P[gm1], g, D, S, bcons, tau, sig);
+  z.cons[(size_t)CRHO * N] = D;
+  for (int a = 0; a < 3; ++a) z.cons[(size_t)(CMOM + a) * N] = S[a];
+  z.cons[(size_t)CENG * N] = tau;
+  if (MHD)
+    for (int a = 0; a < 3; ++a) z.cons[(size_t)(CB + a) * N] = bcons[a];
+  for (int a = 0; a < ndim; ++a) z.csig[(size_t)a * N] = sig[a];
+}
+
+template <bool MHD>
+__global__ void p2c_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  const pb_block_t &blk = pack.blocks[b];
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  p2c_zone_global<MHD>(cfg, g, z, L.ndim);
+}
+
+// ------------------------------------------------------------------ physical boundaries
+// Ghost fill (ref: src/phoebus_boundaries/phoebus_boundaries.cpp:44-270) + ConvertBoundaryConditions
+// (ref: :303-448) in ONE pass. The reference applies the faces ix1,ox1,ix2,ox2,ix3,ox3 one after the
+// other over the entire transverse extent, so an edge/corner ghost zone ends up holding the value
+// its LAST face copied from a zone that an EARLIER face had filled. Each thread here composes that
+// chain for its own ghost zone (x3 map, then x2, then x1 to find the source; factors applied in the
+// reference's order x1, x2, x3), which makes the fill race-free and single-launch. The conversion
+// (inflow check, p2c of the prim-filled ghosts) is pointwise and follows in the same thread.
+template <bool MHD>
+__global__ void bc_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                          unsigned long long *err_count) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const pb_block_t &blk = pack.blocks[b];
+  const int lo[3] = {L.is, L.js, L.ks}, hi[3] = {L.ie, L.je, L.ke};
+  const int idx[3] = {i, j, k};
+  // which face region (if any) contains this zone in each direction
+  int face[3], nphys = 0, nconv = 0;
+  for (int d = 0; d < 3; ++d) {
+    face[d] = -1;
+    if (d >= L.ndim) continue;
+    if (idx[d] < lo[d]) face[d] = 2 * d;
+    else if (idx[d] > hi[d]) face[d] = 2 * d + 1;
+    if (face[d] >= 0) {
+      if (blk.bc[face[d]] > 0) nphys++;
+      if (blk.bc[face[d]] != 0) nconv++;
+    }
+  }
+  if (nconv == 0) return;
+  const int N = L.ncell;
+  const int o = L.idx(k, j, i);
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  if (nphys > 0) {
+    // source chain: cur[3] = zone read by the x3 step, cur[2] by the x2 step, ...
+    int c3[3] = {i, j, k}, c2[3], c1[3], c0[3];
+    auto map = [&](int d, const int in[3], int out[3]) {
+      out[0] = in[0]; out[1] = in[1]; out[2] = in[2];
+      const int f = face[d];
+      if (f < 0 || blk.bc[f] <= 0) return false;
+      // membership is decided on the ORIGINAL zone: maps only change coordinate d
+      const int outer = f & 1;
+      const int ref = outer ? hi[d] : lo[d];
+      if (blk.bc[f] == PB_BC_OUTFLOW) out[d] = ref;
+      else out[d] = 2 * ref + (outer ? 1 : -1) - in[d];
+      return true;
+    };
+    const bool m3 = map(2, c3, c2);
+    const bool m2 = map(1, c2, c1);
+    const bool m1 = map(0, c1, c0);
+    const int src = L.idx(c0[2], c0[1], c0[0]);
+    const bool act[3] = {m1, m2, m3};
+    const int *dstc[3] = {c1, c2, c3}; // destination zone of the step in direction d
+    const int *srcc[3] = {c0, c1, c2};
+    if (cfg.bc_prim) {
+      Real P[NP];
+      load_comps<NP>(pack.prim + (size_t)b * NP * N + src, N, P);
+      for (int d = 0; d < 3; ++d) {
+        if (!act[d]) continue;
+        const int bc = blk.bc[face[d]];
+        for (int n = 0; n < NP; ++n) {
+          Real sgn = 1.0;
+          if (bc == PB_BC_REFLECT) {
+            if ((n >= PVEL && n < PVEL + 3 && n - PVEL == d) || (MHD && n >= PB_ && n < PB_ + 3 && n - PB_ == d)) sgn = -1.0;
+          } else if (bc == PB_BC_POLAR) {
+            if (n == PVEL + 1 || (MHD && n == PB_ + 1)) sgn = -1.0;
+          }
+          P[n] = sgn * P[n];
+        }
+      }
+      store_comps<NP>(z.prim, N, P);
+      *z.temp = pack.temp[(size_t)b * N + src];
+      *z.mu = pack.c2p_mu[(size_t)b * N + src];
+      *z.fail = pack.fail[(size_t)b * N + src];
+      // cons are copied too but overwritten by the p2c below (every physical face is "!= block")
+    } else {
+      Real U[NCn];
+      load_comps<NCn>(cons + (size_t)b * NCn * N + src, N, U);
+      for (int d = 0; d < 3; ++d) {
+        if (!act[d]) continue;
+        const int bc = blk.bc[face[d]];
+        const Real gd = gt.at(0, G_DETGAM, gt.cell(dstc[d][2], dstc[d][1], dstc[d][0]));
+        const Real gs = gt.at(0, G_DETGAM, gt.cell(srcc[d][2], srcc[d][1], srcc[d][0]));
+        const Real gratio = ratio(gd, gs);
+        for (int n = 0; n < NCn; ++n) {
+          Real sgn = 1.0;
+          if (bc == PB_BC_REFLECT && ((n >= CMOM && n < CMOM + 3 && n - CMOM == d) || (MHD && n >= CB && n - CB == d))) sgn = -1.0;
+          if (bc == PB_BC_OUTFLOW && d == 0) U[n] = gratio * U[n];
+          else U[n] = sgn * gratio * U[n];
+        }
+      }
+      store_comps<NCn>(z.cons, N, U);
+    }
+  }
+  // ---- ConvertBoundaryConditions (pointwise)
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  bool did_p2c = false;
+  if (cfg.ox1_inflow_check && blk.bc[1] != 0 && face[0] == 1) {
+    if (!cfg.bc_prim) {
+      const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+      Real U[NCn], P[NP];
+      load_comps<NCn>(z.cons, N, U);
+      const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, L.ndim, U, P, err_count);
+      *z.fail = ok ? 1.0 : 0.0;
+    }
+    Real vcon[3] = {z.prim[(size_t)PVEL * N], z.prim[(size_t)(PVEL + 1) * N], z.prim[(size_t)(PVEL + 2) * N]};
+    Real W = lorentz_factor(vcon, g);
+    const Real ucon1 = vcon[0] - W * g.beta[0] / g.alpha;
+    if (ucon1 < 0) {
+      for (int a = 0; a < 3; ++a) vcon[a] /= W;
+      vcon[0] = g.beta[0] / g.alpha;
+      Real vsq = 0.;
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) vsq += g.g4(a + 1, c + 1) * vcon[a] * vcon[c];
+      W = 1. / sqrt(1. - vsq);
+      for (int a = 0; a < 3; ++a) z.prim[(size_t)(PVEL + a) * N] = W * vcon[a];
+    }
+    p2c_zone_global<MHD>(cfg, g, z, L.ndim);
+    did_p2c = true;
+  }
+  if (cfg.bc_prim && !did_p2c) p2c_zone_global<MHD>(cfg, g, z, L.ndim);
+}
+
+// ------------------------------------------------------------------ EstimateTimestep
+// ref: src/fluid/fluid.cpp:899-944 (without cfl); positive doubles order like their bit patterns
+__global__ void dt_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Region reg, int has_face_speeds,
+                          Real *dt_out) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  Real my = DBL_MAX;
+  if (zone_of_thread(reg, pack.nblocks, b, k, j, i)) {
+    const int o = L.idx(k, j, i);
+    const int N = L.ncell;
+    const int st[3] = {1, L.ni, L.ni * L.nj};
+    const pb_block_t &blk = pack.blocks[b];
+    const Real *cs = pack.csig + (size_t)b * L.ndim * N + o;
+    const Real *fs = pack.fsig + (size_t)b * L.ndim * N + o;
+    Real ldt = 0.0;
+    for (int d = 0; d < L.ndim; d++) {
+      Real max_s = cs[(size_t)d * N];
+      if (has_face_speeds) max_s = dmax(max_s, dmax(fs[(size_t)d * N], fs[(size_t)d * N + st[d]]));
+      ldt += max_s / blk.dx[d];
+    }
+    my = 1.0 / (ldt + 1.e-50);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    const Real other = __shfl_xor_sync(0xffffffffu, my, off);
+    my = dmin(my, other);
+  }
+  __shared__ Real s_min[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_min[warp] = my;
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    my = lane < nw ? s_min[lane] : DBL_MAX;
+    for (int off = 16; off > 0; off >>= 1) my = dmin(my, __shfl_xor_sync(0xffffffffu, my, off));
+    if (lane == 0) atomicMin(reinterpret_cast<unsigned long long *>(dt_out), (unsigned long long)__double_as_longlong(my));
+  }
+}
+
+static unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+static Region entire(const Lay &L) { return Region{0, L.ni - 1, 0, L.nj - 1, 0, L.nk - 1}; }
+static Region interior(const Lay &L) { return Region{L.is, L.ie, L.js, L.je, L.ks, L.ke}; }
+
+static unsigned long long *g_err_count = nullptr; // device counter of unbracketed roots
+unsigned long long *err_counter() {
+  if (!g_err_count) {
+    if (cudaMalloc(&g_err_count, sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    cudaMemset(g_err_count, 0, sizeof(unsigned long long));
+  }
+  return g_err_count;
+}
+
+} // namespace pb
+
+using namespace pb;
+
+extern "C" int pb_cons_to_prim(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
+                               const int jb[2], const int kb[2], void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cons) return set_error(PB_EINVAL, "cons is NULL");
+  const Region reg{ib[0], ib[1], jb[0], jb[1], kb[0], kb[1]};
+  if (reg.n() <= 0) return PB_OK;
+  const int T = zone_threads();
+  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) c2p_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter());
+  else c2p_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter());
+  return check_launch("c2p_kernel");
+}
+
+extern "C" int pb_c2p_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cfg->enable_c2p_fixup) return PB_OK; // ref: fixup_c2p.cpp:60-62
+  const Lay L(*cfg);
+  const Region reg = interior(L);
+  const int T = zone_threads();
+  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) c2p_fixup_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg);
+  else c2p_fixup_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg);
+  return check_launch("c2p_fixup_kernel");
+}
+
+extern "C" int pb_apply_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons,
+                               unsigned long long *counters, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cfg->enable_floors) return PB_OK; // ref: fixup.cpp:293-295
+  const Lay L(*cfg);
+  const Region reg = entire(L);
+  const int T = zone_threads();
+  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) floors_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, counters);
+  else floors_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, counters);
+  return check_launch("floors_kernel");
+}
+
+extern "C" int pb_prim_to_cons(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
+                               const int jb[2], const int kb[2], void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  const Region reg{ib[0], ib[1], jb[0], jb[1], kb[0], kb[1]};
+  if (reg.n() <= 0) return PB_OK;
+  const int T = zone_threads();
+  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) p2c_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg);
+  else p2c_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg);
+  return check_launch("p2c_kernel");
+}
+
+extern "C" int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  const Lay L(*cfg);
+  const Region reg = entire(L);
+  const int T = zone_threads();
+  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) bc_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter());
+  else bc_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter());
+  return check_launch("bc_kernel");
+}
+
+extern "C" int pb_estimate_dt(const pb_pack_t *pack, const pb_cfg_t *cfg, int has_face_speeds, double *dt_out,
+                              void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  const Lay L(*cfg);
+  const Region reg = interior(L);
+  const int T = 256;
+  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  dt_kernel<<<grid, T, 0, (cudaStream_t)stream>>>(*pack, *cfg, reg, has_face_speeds, dt_out);
+  return check_launch("dt_kernel");
+}

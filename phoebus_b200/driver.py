@@ -1,0 +1,119 @@
+"""FluidDriver: sequences the fluid-only sub-graph of PhoebusDriver::RungeKuttaStage
+(ref: src/phoebus_driver.cpp:204-738) over a MeshPack through the C ABI, and the
+time-step control of Parthenon's EvolutionDriver (ref: external/parthenon/src/driver/driver.cpp:210-240,
+src/phoebus_driver.cpp:121-132).
+
+One process per GPU. With world > 1 the ghost exchange of region 8 is: local ghost copy + pack of
+the per-peer send buffers -> NCCL send/recv (torch.distributed batch_isend_irecv) -> unpack.
+"""
+import ctypes as C
+
+from . import _lib
+
+
+class FluidDriver:
+    def __init__(self, mesh, dist=None):
+        self.m = mesh
+        self.L = _lib.lib()
+        self.torch = mesh.torch
+        self.dist = dist if mesh.world > 1 else None
+        self.betas = mesh.p.rk_betas()
+        self.names = ["base"] + ["1"] * (len(self.betas) - 1) + ["base"]  # ref: staged_integrator.cpp:23-29
+        self.has_face_speeds = False
+        self.first_step = True
+        self.dt = None
+        self.ncycle = 0
+        self.time = 0.0
+        self.launches = 0
+        if self.dist is not None:
+            self._setup_halo_buffers()
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def _pk(self):
+        return C.byref(self.m.pack), C.byref(self.m.cfg)
+
+    def _setup_halo_buffers(self):
+        t, m = self.torch, self.m
+        self.halo = []
+        for peer, ((splan, sn), (rplan, rn)) in sorted(m.halo_plans().items()):
+            self.halo.append(dict(
+                peer=peer,
+                splan=t.from_numpy(splan.copy()).to(m.device), nsend=len(splan),
+                rplan=t.from_numpy(rplan.copy()).to(m.device), nrecv=len(rplan),
+                sbuf=t.empty(sn, dtype=t.float64, device=m.device),
+                rbuf=t.empty(rn, dtype=t.float64, device=m.device)))
+
+    # ------------------------------------------------------------------ tasks
+    def exchange(self, cons):
+        """region 8: SendBoundBufs / ReceiveBoundBufs / SetBounds"""
+        m, L = self.m, self.L
+        pk, cfg = self._pk()
+        s = self._stream()
+        if self.dist is None:
+            _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
+            return
+        dist = self.dist
+        for h in self.halo:
+            _lib.check(L.pb_halo_pack(pk, cfg, cons.data_ptr(), h["splan"].data_ptr(), h["nsend"], h["sbuf"].data_ptr(), s),
+                       "pb_halo_pack")
+        ops = []
+        for h in self.halo:
+            ops.append(dist.P2POp(dist.isend, h["sbuf"], h["peer"]))
+            ops.append(dist.P2POp(dist.irecv, h["rbuf"], h["peer"]))
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        # same-GPU neighbours while the NVLink transfers are in flight
+        _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
+        for r in reqs:
+            r.wait()
+        for h in self.halo:
+            _lib.check(L.pb_halo_unpack(pk, cfg, cons.data_ptr(), h["rplan"].data_ptr(), h["nrecv"], h["rbuf"].data_ptr(), s),
+                       "pb_halo_unpack")
+
+    def stage(self, stage, dt):
+        m, L = self.m, self.L
+        pk, cfg = self._pk()
+        s = self._stream()
+        beta = self.betas[stage - 1]
+        sc0, sc1 = m.cons[self.names[stage - 1]], m.cons[self.names[stage]]
+        base = m.cons["base"]
+        cnt = C.c_void_p(m.counters.data_ptr())
+        if self.dist is None:
+            _lib.check(L.pb_rk_stage(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s), "pb_rk_stage")
+        else:
+            _lib.check(L.pb_rk_stage_pre(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s),
+                       "pb_rk_stage_pre")
+            self.exchange(sc1)
+            _lib.check(L.pb_rk_stage_post(pk, cfg, sc1.data_ptr(), cnt, s), "pb_rk_stage_post")
+
+    def estimate_dt(self):
+        """cfl * min over blocks of fluid::EstimateTimestepBlock (ref: src/fluid/fluid.cpp:899-944),
+        MPI_Allreduce(MIN) over ranks (ref: parthenon driver.cpp:237)."""
+        m, L = self.m, self.L
+        pk, cfg = self._pk()
+        m.dt_dev.fill_(1.7976931348623157e308)
+        _lib.check(L.pb_estimate_dt(pk, cfg, int(self.has_face_speeds), m.dt_dev.data_ptr(), self._stream()), "pb_estimate_dt")
+        self.has_face_speeds = True
+        if self.dist is not None:
+            self.dist.all_reduce(m.dt_dev, op=self.dist.ReduceOp.MIN)
+        return m.p.cfl * float(m.dt_dev.item())
+
+    def step(self, dt=None):
+        """One cycle: all RK stages, then the next dt proposal (2x growth limiter)."""
+        if dt is None:
+            dt = self.dt
+            if self.first_step:  # ref: src/phoebus_driver.cpp:121-132
+                dt *= self.m.p.dt_init_fact
+        self.first_step = False
+        for s in range(1, len(self.betas) + 1):
+            self.stage(s, dt)
+        self.ncycle += 1
+        self.time += dt
+        return dt
+
+    def propose_dt(self, dt_prev):
+        """ref: external/parthenon/src/driver/driver.cpp:216-240"""
+        self.dt = min(2.0 * dt_prev, self.estimate_dt())
+        return self.dt

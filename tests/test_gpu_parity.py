@@ -1,0 +1,224 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(include/phoebus_b200.h), against
+  (1) the UNMODIFIED reference's per-stage field dumps (tests/golden/*.npz), every field of every
+      MeshBlock, ghosts included, after every RK stage, and
+  (2) the CPU oracle (oracle/liboracle.so), task by task on the same inputs.
+
+Bar: bit-exact (np.array_equal). The library is compiled with --fmad=false and all
+transcendentals are tabulated on the host, so nothing on the device path differs from the
+reference's IEEE +,-,*,/,sqrt sequence. TOL documents the contractual bound (BASELINE.json:
+1e-12 relative) that the bit-exact check implies.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import from_dump as fd, pyoracle as po
+from tests.helpers import (CASES, block_lx, getter, load_case, load_product_state, oracle_mesh, product_mesh,
+                           stage_tags)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+FIELDS = ("prim", "temp", "c2p_mu", "fail", "csig")
+
+
+def _dev():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch.device("cuda:0")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _setup(name):
+    from phoebus_b200.driver import FluidDriver
+    g, p = load_case(name)
+    mesh, fp = product_mesh(g, device=_dev())
+    order = load_product_state(mesh, g, "init")
+    drv = FluidDriver(mesh)
+    drv.has_face_speeds = True
+    return g, p, mesh, drv, order
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_stages_match_reference_dumps(name):
+    g, p, mesh, drv, order = _setup(name)
+    for tag in stage_tags(g):
+        man = g.manifest(tag)
+        drv.stage(man["stage"], man["dt"])
+        mesh.torch.cuda.synchronize()
+        for mb in man["blocks"]:
+            n = order[mb["gid"]]
+            ref = fd.ref_state(getter(g, tag), mb["gid"], mesh.shape, man["sc1"])
+            for k in FIELDS:
+                mine = _np(getattr(mesh, k)[n]).reshape(ref[k].shape)
+                assert fd.relerr(mine, ref[k]) <= TOL, (name, tag, mb["gid"], k, fd.relerr(mine, ref[k]))
+                assert np.array_equal(mine, ref[k], equal_nan=True), (name, tag, mb["gid"], k, fd.relerr(mine, ref[k]))
+            mine = _np(mesh.cons[man["sc1"]][n])
+            assert np.array_equal(mine, ref["cons"], equal_nan=True), (name, tag, mb["gid"], "cons", fd.relerr(mine, ref["cons"]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_floor_and_failure_counts_match_oracle(name):
+    """identical floor / ceiling / in-kernel-c2p-failure zone counts (BASELINE.json north_star)"""
+    g, p, mesh, drv, order = _setup(name)
+    om = oracle_mesh(g, p)
+    for tag in stage_tags(g):
+        man = g.manifest(tag)
+        drv.stage(man["stage"], man["dt"])
+        om.stage(man["stage"], man["dt"])
+    mesh.torch.cuda.synchronize()
+    mine = _np(mesh.counters)
+    assert np.array_equal(mine, om.counters), (mine, om.counters)
+    nfail = sum(int((b.fail == 0).sum()) for b in om.blocks)
+    assert int((_np(mesh.fail) == 0).sum()) == nfail
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_dt_matches_reference(name):
+    g, p, mesh, drv, order = _setup(name)
+    tags = stage_tags(g)
+    for n, tag in enumerate(tags):
+        man = g.manifest(tag)
+        drv.stage(man["stage"], man["dt"])
+        if man["stage"] == 2 and n + 1 < len(tags):
+            nxt = g.manifest(tags[n + 1])["dt"]
+            assert min(2.0 * man["dt"], drv.estimate_dt()) == nxt
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tasks_match_oracle(name):
+    """each C-ABI task on its own against the oracle's restatement of the same reference
+    function, first stage from the reference's initial state"""
+    import torch
+    from phoebus_b200 import _lib
+    g, p, mesh, drv, order = _setup(name)
+    om = oracle_mesh(g, p)
+    L, OL = _lib.lib(), po.lib()
+    pk, cfg = C.byref(mesh.pack), C.byref(mesh.cfg)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    inv = {n: gid for gid, n in order.items()}
+    ob = {b_gid: b for b_gid, b in zip([mb["gid"] for mb in g.manifest("init")["blocks"]], om.blocks)}
+    blocks = [(n, ob[inv[n]]) for n in range(mesh.nblocks)]
+    nb = mesh.nblocks
+    gsrc = torch.zeros((nb, 4) + mesh.shape, dtype=torch.float64, device=mesh.device)
+    dudt = torch.zeros((nb, mesh.ncons) + mesh.shape, dtype=torch.float64, device=mesh.device)
+    ng, ndim = mesh.ng, mesh.ndim
+    inter = tuple(slice(ng, -ng) if d < ndim else slice(None) for d in (2, 1, 0))
+    man1 = g.manifest(stage_tags(g)[0])
+    dt = man1["dt"]
+
+    # --- sources, fluxes, CT, FixFluxes, divergence
+    _lib.check(L.pb_source_terms(pk, cfg, gsrc.data_ptr(), s))
+    _lib.check(L.pb_calculate_fluxes(pk, cfg, s))
+    torch.cuda.synchronize()
+    for n, b in blocks:
+        c = C.byref(b.cfg)
+        OL.orc_source_terms(c, b.geom, b.prim, b.gsrc)
+        OL.orc_calculate_fluxes(c, b.geom, b.prim, b.flux, b.fsig)
+        assert np.array_equal(_np(gsrc[n])[(slice(None),) + inter], b.gsrc[(slice(None),) + inter])
+        assert np.array_equal(_np(mesh.flux[n]), b.flux), fd.relerr(_np(mesh.flux[n]), b.flux)
+        assert np.array_equal(_np(mesh.fsig[n]), b.fsig)
+    _lib.check(L.pb_flux_ct(pk, cfg, s))
+    _lib.check(L.pb_fix_fluxes(pk, cfg, s))
+    _lib.check(L.pb_flux_divergence(pk, cfg, dudt.data_ptr(), s))
+    torch.cuda.synchronize()
+    for n, b in blocks:
+        c = C.byref(b.cfg)
+        OL.orc_flux_ct(c, b.flux, b.emf)
+        OL.orc_fix_fluxes(c, b.flux)
+        OL.orc_flux_divergence(c, b.flux, b.dudt)
+        assert np.array_equal(_np(mesh.flux[n]), b.flux)
+        assert np.array_equal(_np(mesh.emf[n]), b.emf)
+        assert np.array_equal(_np(dudt[n])[(slice(None),) + inter], b.dudt[(slice(None),) + inter])
+    # --- fused update == divergence + SumData + Average + Update, interior and ghosts
+    base, one = mesh.cons["base"], mesh.cons["1"]
+    dudt2 = torch.zeros_like(dudt)
+    _lib.check(L.pb_update_fused(pk, cfg, base.data_ptr(), base.data_ptr(), 1.0, dt, one.data_ptr(), dudt2.data_ptr(), None, s))
+    torch.cuda.synchronize()
+    for n, b in blocks:
+        c = C.byref(b.cfg)
+        u0 = b.cons["base"]
+        OL.orc_rk_update(c, b.dudt, b.gsrc.ctypes.data, u0, u0.copy(), 1.0, dt, b.cons["1"])
+        assert np.array_equal(_np(one[n]), b.cons["1"])
+        assert np.array_equal(_np(dudt2[n])[(slice(None),) + inter], b.dudt[(slice(None),) + inter])
+    # --- separate WeightedSumData entry point
+    z = torch.empty_like(base)
+    _lib.check(L.pb_weighted_sum(base.data_ptr(), one.data_ptr(), 0.5, 0.5, z.data_ptr(), base.numel(), s))
+    torch.cuda.synchronize()
+    assert np.array_equal(_np(z), 0.5 * _np(base) + 0.5 * _np(one))
+    # --- stale fixup + floors, halo, BCs, c2p, fixup, floors: one at a time
+    cnt = torch.zeros(3, dtype=torch.int64, device=mesh.device)
+    ocnt = np.zeros(3, dtype=np.int64)
+
+    def compare(what):
+        torch.cuda.synchronize()
+        for n, b in blocks:
+            for k in FIELDS:
+                assert np.array_equal(_np(getattr(mesh, k)[n]).reshape(getattr(b, k).shape), getattr(b, k), equal_nan=True), (what, k)
+            assert np.array_equal(_np(one[n]), b.cons["1"], equal_nan=True), (what, "cons")
+    _lib.check(L.pb_c2p_fixup(pk, cfg, one.data_ptr(), s))
+    for n, b in blocks:
+        OL.orc_c2p_fixup(C.byref(b.cfg), b.geom, b.cons["1"], b.prim, b.temp, b.fail, b.csig)
+    compare("stale fixup")
+    _lib.check(L.pb_apply_floors(pk, cfg, one.data_ptr(), cnt.data_ptr(), s))
+    for n, b in blocks:
+        OL.orc_apply_floors(C.byref(b.cfg), b.geom, b.cons["1"], b.prim, b.temp, b.c2p_mu, b.csig, ocnt.ctypes.data)
+    compare("stale floors")
+    _lib.check(L.pb_halo_exchange_local(pk, cfg, one.data_ptr(), s))
+    om.exchange("1")
+    compare("halo")
+    _lib.check(L.pb_apply_bcs(pk, cfg, one.data_ptr(), s))
+    for n, b in blocks:
+        for _ in range(2):
+            OL.orc_apply_bcs(C.byref(b.cfg), b.geom, b.cons["1"], b.prim, b.temp, b.c2p_mu, b.fail, b.csig)
+    compare("bcs")
+    I2 = C.c_int * 2
+    ib, jb, kb = I2(0, mesh.ni - 1), I2(0, mesh.nj - 1), I2(0, mesh.nk - 1)
+    _lib.check(L.pb_cons_to_prim(pk, cfg, one.data_ptr(), ib, jb, kb, s))
+    for n, b in blocks:
+        OL.orc_cons_to_prim(C.byref(b.cfg), b.geom, b.cons["1"], b.prim, b.temp, b.c2p_mu, b.fail, b.csig, *b.entire())
+    compare("c2p")
+    _lib.check(L.pb_c2p_fixup(pk, cfg, one.data_ptr(), s))
+    _lib.check(L.pb_apply_floors(pk, cfg, one.data_ptr(), cnt.data_ptr(), s))
+    for n, b in blocks:
+        OL.orc_c2p_fixup(C.byref(b.cfg), b.geom, b.cons["1"], b.prim, b.temp, b.fail, b.csig)
+        OL.orc_apply_floors(C.byref(b.cfg), b.geom, b.cons["1"], b.prim, b.temp, b.c2p_mu, b.csig, ocnt.ctypes.data)
+    compare("fixup+floors")
+    assert np.array_equal(_np(cnt), ocnt)
+    # --- p2c(c2p(U)) round trip on the interior through the PrimitiveToConserved entry point
+    two = one.clone()
+    _lib.check(L.pb_prim_to_cons(pk, cfg, two.data_ptr(), ib, jb, kb, s))
+    torch.cuda.synchronize()
+    for n, b in blocks:
+        cons = b.cons["1"].copy()
+        csig = b.csig.copy()
+        OL.orc_prim_to_cons(C.byref(b.cfg), b.geom, b.prim, cons, csig, *b.entire())
+        assert np.array_equal(_np(two[n]), cons, equal_nan=True)
+
+
+def test_recon_schemes_through_flux_kernel():
+    """all four reconstructions x both Riemann solvers on the 3-D blast fixture's state"""
+    import torch
+    from phoebus_b200 import _lib
+    g, p, mesh, drv, order = _setup("blast3d")
+    om = oracle_mesh(g, p)
+    L, OL = _lib.lib(), po.lib()
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for recon in range(4):
+        for riemann in range(2):
+            mesh.cfg.recon, mesh.cfg.riemann = recon, riemann
+            mesh.flux.zero_()
+            mesh.fsig.zero_()
+            _lib.check(L.pb_calculate_fluxes(C.byref(mesh.pack), C.byref(mesh.cfg), s))
+            torch.cuda.synchronize()
+            for n, b in enumerate(om.blocks):
+                b.cfg.recon, b.cfg.riemann = recon, riemann
+                b.flux[:] = 0
+                b.fsig[:] = 0
+                OL.orc_calculate_fluxes(C.byref(b.cfg), b.geom, b.prim, b.flux, b.fsig)
+                assert np.array_equal(_np(mesh.flux[n]), b.flux), (recon, riemann, fd.relerr(_np(mesh.flux[n]), b.flux))
+                assert np.array_equal(_np(mesh.fsig[n]), b.fsig)
