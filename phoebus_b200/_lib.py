@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libphoebus_b200.so")
+LIB_PATH = os.environ.get("PHOEBUS_B200_LIB") or os.path.join(HERE, "libphoebus_b200.so")  # env override: tuning variants
 
 PB_NGLOC, PB_NGDER = 21, 33
 PB_GEOM_WORDS = 4 * PB_NGLOC + PB_NGDER

@@ -49,7 +49,7 @@ int flux_threads_target() {
 }
 int zone_threads() {
   static int v = env_int("PB_ZONE_THREADS", 128);
-  return v;
+  return v > 128 ? 128 : v; // zone kernels are compiled with __launch_bounds__(128, n)
 }
 
 } // namespace pb

@@ -19,8 +19,9 @@ struct FluxTile {
   int tiles;   // CTAs per block
 };
 
+// 2 CTAs of <= 288 threads per SM: 96 registers (measured optimum on B200, profiles/r1_tuning.md)
 template <int DIR, int RECON, bool MHD>
-__global__ void flux_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const FluxTile ft) {
+__global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const FluxTile ft) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   extern __shared__ Real s_ql[]; // [NP][(NS+1)*TT]
   const Lay L(cfg);
@@ -143,7 +144,8 @@ static int launch_dir(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s
   ft.TT = target / ft.NS;
   if (ft.TT < 1) ft.TT = 1;
   if (ft.TT > ft.nT) ft.TT = ft.nT;
-  if (ft.NS * ft.TT > 1024) return set_error(PB_EINVAL, "block too large for the flux tile");
+  while (ft.NS * ft.TT > 288 && ft.TT > 1) ft.TT--;
+  if (ft.NS * ft.TT > 288) return set_error(PB_EINVAL, "block too large for the flux tile");
   ft.tiles = (ft.nT + ft.TT - 1) / ft.TT;
   const int threads = ft.NS * ft.TT;
   const size_t smem = (size_t)NC<MHD>::nprim * (ft.NS + 1) * ft.TT * sizeof(Real);

@@ -297,7 +297,7 @@ template <bool MHD> __global__ void source_kernel(const pb_pack_t pack, const pb
 // (AverageIndependentData); uout = 1*u_avg + bdt*dudt (UpdateIndependentData).
 // ref: src/phoebus_driver.cpp:560-576, external/parthenon/src/interface/update.hpp:71-136
 template <bool MHD>
-__global__ void update_fused_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *u0, const Real *ubase,
+__global__ void __launch_bounds__(128, 5) update_fused_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *u0, const Real *ubase,
                                     Real beta, Real bdt, Real *uout, Real *dudt_out, Real *gsrc_out) {
   constexpr int NCn = NC<MHD>::ncons, NP = NC<MHD>::nprim;
   const Lay L(cfg);

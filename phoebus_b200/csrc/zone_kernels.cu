@@ -96,7 +96,7 @@ PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const Point
 // ------------------------------------------------------------------ ConToPrim::Solve
 // ref: src/fluid/fluid.cpp:477-517
 template <bool MHD>
-__global__ void c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+__global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
                            unsigned long long *err_count) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   const Lay L(cfg);
@@ -118,7 +118,7 @@ __global__ void c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons,
 // ------------------------------------------------------------------ ConToPrim::Solve fixup
 // ref: src/fixup/fixup_c2p.cpp:170-353
 template <bool MHD>
-__global__ void c2p_fixup_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg) {
+__global__ void __launch_bounds__(128, 4) c2p_fixup_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg) {
   constexpr int NP = NC<MHD>::nprim, prs = NC<MHD>::prs, gm1 = NC<MHD>::gm1;
   const Lay L(cfg);
   int b, k, j, i;
@@ -187,7 +187,7 @@ __global__ void c2p_fixup_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real 
 // ------------------------------------------------------------------ ApplyFloors
 // ref: src/fixup/fixup.cpp:370-684 (fluid part)
 template <bool MHD>
-__global__ void floors_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+__global__ void __launch_bounds__(128, 5) floors_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
                               unsigned long long *counters) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons, prs = NC<MHD>::prs, gm1 = NC<MHD>::gm1;
   const Lay L(cfg);
@@ -354,7 +354,7 @@ __global__ void p2c_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons,
 // reference's order x1, x2, x3), which makes the fill race-free and single-launch. The conversion
 // (inflow check, p2c of the prim-filled ghosts) is pointwise and follows in the same thread.
 template <bool MHD>
-__global__ void bc_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+__global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
                           unsigned long long *err_count) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   const Lay L(cfg);

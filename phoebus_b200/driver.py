@@ -25,6 +25,7 @@ class FluidDriver:
         self.ncycle = 0
         self.time = 0.0
         self.launches = 0
+        self.timers = None  # dict -> per-task CUDA-event timing (bench.py)
         if self.dist is not None:
             self._setup_halo_buffers()
 
@@ -80,6 +81,8 @@ class FluidDriver:
         sc0, sc1 = m.cons[self.names[stage - 1]], m.cons[self.names[stage]]
         base = m.cons["base"]
         cnt = C.c_void_p(m.counters.data_ptr())
+        if self.timers is not None:
+            return self._stage_timed(stage, dt)
         if self.dist is None:
             _lib.check(L.pb_rk_stage(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s), "pb_rk_stage")
         else:
@@ -87,6 +90,64 @@ class FluidDriver:
                        "pb_rk_stage_pre")
             self.exchange(sc1)
             _lib.check(L.pb_rk_stage_post(pk, cfg, sc1.data_ptr(), cnt, s), "pb_rk_stage_post")
+        self.launches += self.LAUNCHES_PER_STAGE
+
+    # kernels launched per stage by pb_rk_stage: flux x ndim, emf + ct, fix, update + ghosts,
+    # fixup, floors, halo, bcs, c2p, fixup, floors
+    @property
+    def LAUNCHES_PER_STAGE(self):
+        m = self.m
+        n = m.ndim + 2 + 1 + 1 + 1
+        if m.p.mhd and m.ndim > 1:
+            n += 2
+        if m.p.enable_flux_fixup:
+            n += 1
+        if m.p.enable_c2p_fixup:
+            n += 2
+        if m.p.enable_floors:
+            n += 2
+        return n
+
+    def _stage_timed(self, stage, dt):
+        """Same task order as pb_rk_stage, one C-ABI call per task, CUDA events around each task
+        group on the launching stream (bench.py's per-kernel durations)."""
+        m, L = self.m, self.L
+        pk, cfg = self._pk()
+        s = self._stream()
+        t = self.torch
+        beta = self.betas[stage - 1]
+        sc0, sc1 = m.cons[self.names[stage - 1]], m.cons[self.names[stage]]
+        base = m.cons["base"]
+        cnt = C.c_void_p(m.counters.data_ptr())
+
+        def timed(name, fn):
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            self.timers.setdefault(name, []).append((e0, e1))
+        I2 = C.c_int * 2
+        ib, jb, kb = I2(0, m.ni - 1), I2(0, m.nj - 1), I2(0, m.nk - 1)
+        timed("flux", lambda: _lib.check(L.pb_calculate_fluxes(pk, cfg, s), "pb_calculate_fluxes"))
+        timed("ct_fix", lambda: (_lib.check(L.pb_flux_ct(pk, cfg, s), "pb_flux_ct"),
+                                 _lib.check(L.pb_fix_fluxes(pk, cfg, s), "pb_fix_fluxes")))
+        timed("update", lambda: _lib.check(L.pb_update_fused(pk, cfg, sc0.data_ptr(), base.data_ptr(), beta, beta * dt,
+                                                             sc1.data_ptr(), None, None, s), "pb_update_fused"))
+        timed("stale_fixup_floors", lambda: (_lib.check(L.pb_c2p_fixup(pk, cfg, sc1.data_ptr(), s), "pb_c2p_fixup"),
+                                             _lib.check(L.pb_apply_floors(pk, cfg, sc1.data_ptr(), cnt, s), "pb_apply_floors")))
+        timed("halo", lambda: self.exchange(sc1))
+        timed("bcs", lambda: _lib.check(L.pb_apply_bcs(pk, cfg, sc1.data_ptr(), s), "pb_apply_bcs"))
+        timed("c2p", lambda: _lib.check(L.pb_cons_to_prim(pk, cfg, sc1.data_ptr(), ib, jb, kb, s), "pb_cons_to_prim"))
+        timed("fixup_floors", lambda: (_lib.check(L.pb_c2p_fixup(pk, cfg, sc1.data_ptr(), s), "pb_c2p_fixup"),
+                                       _lib.check(L.pb_apply_floors(pk, cfg, sc1.data_ptr(), cnt, s), "pb_apply_floors")))
+        self.launches += self.LAUNCHES_PER_STAGE
+
+    def timer_summary(self):
+        """name -> (calls, total ms); call after a synchronize"""
+        out = {}
+        for name, evs in (self.timers or {}).items():
+            out[name] = (len(evs), sum(e0.elapsed_time(e1) for e0, e1 in evs))
+        return out
 
     def estimate_dt(self):
         """cfl * min over blocks of fluid::EstimateTimestepBlock (ref: src/fluid/fluid.cpp:899-944),
@@ -96,6 +157,7 @@ class FluidDriver:
         m.dt_dev.fill_(1.7976931348623157e308)
         _lib.check(L.pb_estimate_dt(pk, cfg, int(self.has_face_speeds), m.dt_dev.data_ptr(), self._stream()), "pb_estimate_dt")
         self.has_face_speeds = True
+        self.launches += 1
         if self.dist is not None:
             self.dist.all_reduce(m.dt_dev, op=self.dist.ReduceOp.MIN)
         return m.p.cfl * float(m.dt_dev.item())
