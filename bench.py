@@ -99,6 +99,8 @@ def init_state(mesh, drv):
     base = mesh.cons["base"]
     _lib.check(L.pb_prim_to_cons(pk, cfg, base.data_ptr(), ib, jb, kb, s), "pb_prim_to_cons")
     drv.exchange(base)
+    mesh.invalidate_flags()
+    drv.ensure_flags()
     _lib.check(L.pb_rk_stage_post(pk, cfg, base.data_ptr(), C.c_void_p(mesh.counters.data_ptr()), s), "init c2p")
     mesh.counters.zero_()
 
@@ -139,7 +141,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    drv.timers = {}
+    drv.enable_profile(True)
     launches0 = drv.launches
     mesh.counters.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -157,7 +159,7 @@ def run_ours(args):
     ms_total = float(ms.item())
     launches = drv.launches - launches0
     tsum = drv.timer_summary()
-    drv.timers = None
+    drv.enable_profile(False)
     counters = mesh.counters.clone()
     nfail = (mesh.fail == 0).sum()
     finite = torch.isfinite(mesh.cons["base"]).all() & torch.isfinite(mesh.prim).all()

@@ -101,6 +101,13 @@ typedef struct pb_pack {
   double *fsig;             /* [b][ndim][cells] face_signal_speed */
   double *flux;             /* [b][ndim][ncons][cells] */
   double *emf;              /* [b][3][cells] */
+  /* optional accelerators (NULL / 0: the sequencer falls back to the exhaustive passes) */
+  unsigned char *zflags;    /* [b][cells] zone flags kept by pb_rk_stage*: which zones the fixup / floor
+                             * tasks have to touch; build once with pb_scan_zone_flags */
+  const int *bc_blocks;     /* device [n_bc_blocks]: blocks with a physical or periodic mesh boundary */
+  int n_bc_blocks;
+  double *gsrc;             /* [b][4][cells] the "geometric source terms" container (ref: phoebus_driver.cpp:289-299);
+                             * when present the sequencer runs the sources as their own launch */
 } pb_pack_t;
 
 const char *pb_version(void);
@@ -142,12 +149,18 @@ int pb_source_terms(const pb_pack_t *pack, const pb_cfg_t *cfg, double *gsrc, vo
 int pb_weighted_sum(const double *x, const double *y, double w1, double w2, double *z, long long n,
                     void *stream);
 /* Fusion of FluxDivergence + CalculateFluidSourceTerms + SumData + AverageIndependentData +
- * UpdateIndependentData (ref: src/phoebus_driver.cpp:560-576) on interior zones:
- *   dudt = -div F (+ gsrc on momentum, energy);  uout = (beta*u0 + (1-beta)*ubase) + bdt*dudt.
+ * UpdateIndependentData (ref: src/phoebus_driver.cpp:560-576):
+ *   dudt = -div F (+ gsrc on momentum, energy);  uout = (beta*u0 + (1-beta)*ubase) + bdt*dudt
+ * on interior zones and, if update_ghosts, uout = beta*u0 + (1-beta)*ubase on ghost zones (the
+ * reference's WeightedSumData runs over entire arrays; dUdt is zero outside the interior).
  * dudt_out / gsrc_out may be NULL (not materialised). u0 is NOT averaged in place. */
 int pb_update_fused(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *u0, const double *ubase,
                     double beta, double bdt, double *uout, double *dudt_out, double *gsrc_out,
-                    void *stream);
+                    int update_ghosts, void *stream);
+/* The same update with the sources read from gsrc (written earlier by pb_source_terms). */
+int pb_update_from_sources(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *u0, const double *ubase,
+                           double beta, double bdt, double *uout, const double *gsrc, double *dudt_out,
+                           int update_ghosts, void *stream);
 /* ref: fluid::ConservedToPrimitiveRegion / ConservedToPrimitiveRobust, src/fluid/fluid.cpp:452-517,
  * src/fluid/con2prim_robust.hpp:300-453; inclusive index ranges */
 int pb_cons_to_prim(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
@@ -158,6 +171,9 @@ int pb_c2p_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void 
  * NULL): [0] floors applied, [1] ceilings applied, [2] in-kernel c2p failures; accumulated. */
 int pb_apply_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons,
                     unsigned long long *counters, void *stream);
+/* (Re)build pack->zflags from the current p.* and fail fields: call once before the first
+ * pb_rk_stage* on a pack, and again whenever something else has written p.* or fail. */
+int pb_scan_zone_flags(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream);
 /* ref: fluid::PrimitiveToConservedRegion, src/fluid/fluid.cpp:368-449 */
 int pb_prim_to_cons(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
                     const int jb[2], const int kb[2], void *stream);
@@ -195,6 +211,22 @@ int pb_rk_stage_pre(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc0, dou
                     double beta, double dt, unsigned long long *counters, void *stream);
 int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1,
                      unsigned long long *counters, void *stream);
+
+/* Optional per-task device timing of pb_rk_stage*: CUDA events on the launching stream around each
+ * task group. pb_profile_read synchronises the recorded events, returns the accumulated milliseconds
+ * and call counts per PB_TASK_* and resets the accumulators. */
+#define PB_TASK_FLUX 0
+#define PB_TASK_CT_FIX 1
+#define PB_TASK_SOURCE 2
+#define PB_TASK_UPDATE 3
+#define PB_TASK_STALE_FIXUP_FLOORS 4
+#define PB_TASK_HALO 5
+#define PB_TASK_BCS 6
+#define PB_TASK_C2P 7
+#define PB_TASK_FIXUP_FLOORS 8
+#define PB_NTASK 9
+int pb_profile_enable(int on);
+int pb_profile_read(double ms[PB_NTASK], int calls[PB_NTASK]);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("PHOEBUS_B200_LIB") or os.path.join(HERE, "libphoebus_
 PB_NGLOC, PB_NGDER = 21, 33
 PB_GEOM_WORDS = 4 * PB_NGLOC + PB_NGDER
 PB_NBR_NONE, PB_NBR_REMOTE = -1, -2
+TASK_NAMES = ("flux", "ct_fix", "source", "update", "stale_fixup_floors", "halo", "bcs", "c2p", "fixup_floors")
 
 
 class PbBlock(C.Structure):
@@ -42,7 +43,8 @@ class PbCfg(C.Structure):
 class PbPack(C.Structure):
     _fields_ = [("nblocks", C.c_int), ("blocks", C.c_void_p), ("geom", C.c_void_p), ("floor_tab", C.c_void_p),
                 ("prim", C.c_void_p), ("temp", C.c_void_p), ("c2p_mu", C.c_void_p), ("fail", C.c_void_p),
-                ("csig", C.c_void_p), ("fsig", C.c_void_p), ("flux", C.c_void_p), ("emf", C.c_void_p)]
+                ("csig", C.c_void_p), ("fsig", C.c_void_p), ("flux", C.c_void_p), ("emf", C.c_void_p),
+                ("zflags", C.c_void_p), ("bc_blocks", C.c_void_p), ("n_bc_blocks", C.c_int), ("gsrc", C.c_void_p)]
 
 
 # every symbol include/phoebus_b200.h declares: name -> (restype, argtypes)
@@ -63,10 +65,12 @@ SYMBOLS = {
     "pb_flux_divergence": (C.c_int, [_PACK, _CFG, _P, _P]),
     "pb_source_terms": (C.c_int, [_PACK, _CFG, _P, _P]),
     "pb_weighted_sum": (C.c_int, [_P, _P, C.c_double, C.c_double, _P, C.c_longlong, _P]),
-    "pb_update_fused": (C.c_int, [_PACK, _CFG, _P, _P, C.c_double, C.c_double, _P, _P, _P, _P]),
+    "pb_update_fused": (C.c_int, [_PACK, _CFG, _P, _P, C.c_double, C.c_double, _P, _P, _P, C.c_int, _P]),
+    "pb_update_from_sources": (C.c_int, [_PACK, _CFG, _P, _P, C.c_double, C.c_double, _P, _P, _P, C.c_int, _P]),
     "pb_cons_to_prim": (C.c_int, [_PACK, _CFG, _P, _I2, _I2, _I2, _P]),
     "pb_c2p_fixup": (C.c_int, [_PACK, _CFG, _P, _P]),
     "pb_apply_floors": (C.c_int, [_PACK, _CFG, _P, _P, _P]),
+    "pb_scan_zone_flags": (C.c_int, [_PACK, _CFG, _P]),
     "pb_prim_to_cons": (C.c_int, [_PACK, _CFG, _P, _I2, _I2, _I2, _P]),
     "pb_halo_exchange_local": (C.c_int, [_PACK, _CFG, _P, _P]),
     "pb_halo_nvar": (C.c_int, [_CFG]),
@@ -74,6 +78,8 @@ SYMBOLS = {
     "pb_halo_unpack": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P, _P]),
     "pb_apply_bcs": (C.c_int, [_PACK, _CFG, _P, _P]),
     "pb_estimate_dt": (C.c_int, [_PACK, _CFG, C.c_int, _P, _P]),
+    "pb_profile_enable": (C.c_int, [C.c_int]),
+    "pb_profile_read": (C.c_int, [_P, _P]),
     "pb_rk_stage": (C.c_int, [_PACK, _CFG, _P, _P, _P, C.c_double, C.c_double, _P, _P]),
     "pb_rk_stage_pre": (C.c_int, [_PACK, _CFG, _P, _P, _P, C.c_double, C.c_double, _P, _P]),
     "pb_rk_stage_post": (C.c_int, [_PACK, _CFG, _P, _P, _P]),

@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "pb_device.cuh"
 #include "pb_host.hpp"
@@ -69,32 +70,149 @@ extern "C" int pb_device_sm_count(void) {
   return n;
 }
 
-// ---- stage sequencing, ref: src/phoebus_driver.cpp:204-738 (fluid-only sub-graph)
+// ---- optional per-task device timing of the sequencer (bench.py): CUDA events recorded on the
+// launching stream around each task group; read back (and reset) with pb_profile_read.
+namespace pb {
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[PB_NTASK][2];
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    cudaEvent_t e;
+    if (!pool.empty()) {
+      e = pool.back();
+      pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
+};
+static Profiler g_prof;
+struct ProfScope {
+  int id;
+  cudaStream_t s;
+  ProfScope(int id_, cudaStream_t s_) : id(id_), s(s_) {
+    if (g_prof.on) {
+      cudaEvent_t e = g_prof.get();
+      cudaEventRecord(e, s);
+      g_prof.ev[id][0].push_back(e);
+    }
+  }
+  ~ProfScope() {
+    if (g_prof.on) {
+      cudaEvent_t e = g_prof.get();
+      cudaEventRecord(e, s);
+      g_prof.ev[id][1].push_back(e);
+    }
+  }
+};
+} // namespace pb
+
+extern "C" int pb_profile_enable(int on) {
+  pb::g_prof.on = on != 0;
+  return PB_OK;
+}
+extern "C" int pb_profile_read(double *ms, int *calls) {
+  using namespace pb;
+  for (int t = 0; t < PB_NTASK; ++t) {
+    double tot = 0;
+    const size_t n = g_prof.ev[t][1].size();
+    for (size_t i = 0; i < n; ++i) {
+      float x = 0;
+      cudaEventSynchronize(g_prof.ev[t][1][i]);
+      if (cudaEventElapsedTime(&x, g_prof.ev[t][0][i], g_prof.ev[t][1][i]) == cudaSuccess) tot += x;
+      g_prof.pool.push_back(g_prof.ev[t][0][i]);
+      g_prof.pool.push_back(g_prof.ev[t][1][i]);
+    }
+    g_prof.ev[t][0].clear();
+    g_prof.ev[t][1].clear();
+    if (ms) ms[t] = tot;
+    if (calls) calls[t] = (int)n;
+  }
+  return PB_OK;
+}
+
+namespace pb {
+int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2], const int jb[2], const int kb[2],
+               unsigned char *zflags, cudaStream_t s);
+int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int mode, unsigned char *zflags, cudaStream_t s);
+int launch_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, unsigned long long *counters, int mode,
+                  unsigned char *zflags, const double *lazy_u0, const double *lazy_ubase, double beta, cudaStream_t s);
+} // namespace pb
+
+// ---- stage sequencing, ref: src/phoebus_driver.cpp:204-738 (fluid-only sub-graph).
+// With pack->zflags the fixup / floor tasks only visit the zones they can change (flags maintained by
+// the c2p, fixup and floor kernels themselves) and the ghost zones of the stage-output container are
+// not materialised before the halo exchange overwrites them; results are identical either way
+// (tests/test_gpu_parity.py runs both).
 extern "C" int pb_rk_stage_pre(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc0, double *base, double *sc1,
                                double beta, double dt, unsigned long long *counters, void *stream) {
   int rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool flagged = pack->zflags != nullptr;
   // region 2: CalculateFluxes -> FluxCT -> FixFluxes
-  if ((rc = pb_calculate_fluxes(pack, cfg, stream))) return rc;
-  if ((rc = pb_flux_ct(pack, cfg, stream))) return rc;
-  if ((rc = pb_fix_fluxes(pack, cfg, stream))) return rc;
-  // regions 1 + 6: sources, FluxDivergence, SumData, Average, Update (fused)
-  if ((rc = pb_update_fused(pack, cfg, sc0, base, beta, beta * dt, sc1, nullptr, nullptr, stream))) return rc;
+  {
+    ProfScope p(PB_TASK_FLUX, s);
+    if ((rc = pb_calculate_fluxes(pack, cfg, stream))) return rc;
+  }
+  {
+    ProfScope p(PB_TASK_CT_FIX, s);
+    if ((rc = pb_flux_ct(pack, cfg, stream))) return rc;
+    if ((rc = pb_fix_fluxes(pack, cfg, stream))) return rc;
+  }
+  // regions 1 + 6: sources, FluxDivergence, SumData, Average, Update
+  if (pack->gsrc) {
+    {
+      ProfScope p(PB_TASK_SOURCE, s);
+      if ((rc = pb_source_terms(pack, cfg, pack->gsrc, stream))) return rc;
+    }
+    ProfScope p(PB_TASK_UPDATE, s);
+    if ((rc = pb_update_from_sources(pack, cfg, sc0, base, beta, beta * dt, sc1, pack->gsrc, nullptr, !flagged, stream))) return rc;
+  } else {
+    ProfScope p(PB_TASK_UPDATE, s);
+    if ((rc = pb_update_fused(pack, cfg, sc0, base, beta, beta * dt, sc1, nullptr, nullptr, !flagged, stream))) return rc;
+  }
   // region 7: fixup + floors acting on the previous stage's prims / fail flags
-  if ((rc = pb_c2p_fixup(pack, cfg, sc1, stream))) return rc;
-  if ((rc = pb_apply_floors(pack, cfg, sc1, counters, stream))) return rc;
+  ProfScope p7(PB_TASK_STALE_FIXUP_FLOORS, s);
+  if (flagged) {
+    if ((rc = launch_fixup(pack, cfg, sc1, 2, pack->zflags, s))) return rc;
+    if ((rc = launch_floors(pack, cfg, sc1, counters, 2, pack->zflags, sc0, base, beta, s))) return rc;
+  } else {
+    if ((rc = pb_c2p_fixup(pack, cfg, sc1, stream))) return rc;
+    if ((rc = pb_apply_floors(pack, cfg, sc1, counters, stream))) return rc;
+  }
   return PB_OK;
 }
 
 extern "C" int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, unsigned long long *counters,
                                 void *stream) {
   int rc;
+  cudaStream_t s = (cudaStream_t)stream;
   // region 9: BCs -> c2p over the entire block -> fixup -> floors
-  if ((rc = pb_apply_bcs(pack, cfg, sc1, stream))) return rc;
+  {
+    ProfScope p(PB_TASK_BCS, s);
+    if ((rc = pb_apply_bcs(pack, cfg, sc1, stream))) return rc;
+  }
   const Lay L(*cfg);
   const int ib[2] = {0, L.ni - 1}, jb[2] = {0, L.nj - 1}, kb[2] = {0, L.nk - 1};
-  if ((rc = pb_cons_to_prim(pack, cfg, sc1, ib, jb, kb, stream))) return rc;
-  if ((rc = pb_c2p_fixup(pack, cfg, sc1, stream))) return rc;
-  if ((rc = pb_apply_floors(pack, cfg, sc1, counters, stream))) return rc;
+  if (pack->zflags) {
+    {
+      ProfScope p(PB_TASK_C2P, s);
+      if ((rc = launch_c2p(pack, cfg, sc1, ib, jb, kb, pack->zflags, s))) return rc;
+    }
+    ProfScope p(PB_TASK_FIXUP_FLOORS, s);
+    if ((rc = launch_fixup(pack, cfg, sc1, 1, pack->zflags, s))) return rc;
+    if ((rc = launch_floors(pack, cfg, sc1, counters, 1, pack->zflags, nullptr, nullptr, 1.0, s))) return rc;
+  } else {
+    {
+      ProfScope p(PB_TASK_C2P, s);
+      if ((rc = pb_cons_to_prim(pack, cfg, sc1, ib, jb, kb, stream))) return rc;
+    }
+    ProfScope p(PB_TASK_FIXUP_FLOORS, s);
+    if ((rc = pb_c2p_fixup(pack, cfg, sc1, stream))) return rc;
+    if ((rc = pb_apply_floors(pack, cfg, sc1, counters, stream))) return rc;
+  }
   return PB_OK;
 }
 
@@ -103,6 +221,9 @@ extern "C" int pb_rk_stage(const pb_pack_t *pack, const pb_cfg_t *cfg, double *s
   int rc;
   if ((rc = pb_rk_stage_pre(pack, cfg, sc0, base, sc1, beta, dt, counters, stream))) return rc;
   // region 8: ghost exchange
-  if ((rc = pb_halo_exchange_local(pack, cfg, sc1, stream))) return rc;
+  {
+    ProfScope p(PB_TASK_HALO, (cudaStream_t)stream);
+    if ((rc = pb_halo_exchange_local(pack, cfg, sc1, stream))) return rc;
+  }
   return pb_rk_stage_post(pack, cfg, sc1, counters, stream);
 }

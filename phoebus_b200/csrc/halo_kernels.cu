@@ -40,12 +40,14 @@ static HaloFields halo_fields(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *
 
 __global__ void halo_local_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const HaloFields hf) {
   const Lay L(cfg);
+  const Shell sh(L);
   const int N = L.ncell;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)N * pack.nblocks) return;
-  const int b = (int)(t / N);
-  const int o = (int)(t % N);
-  const int i = o % L.ni, j = (o / L.ni) % L.nj, k = o / (L.ni * L.nj);
+  if (t >= (long long)sh.n * pack.nblocks) return;
+  const int b = (int)(t / sh.n);
+  int i, j, k;
+  sh.cell(L, (int)(t % sh.n), k, j, i);
+  const int o = L.idx(k, j, i);
   const int o1 = i < L.is ? -1 : (i > L.ie ? 1 : 0);
   const int o2 = j < L.js ? -1 : (j > L.je ? 1 : 0);
   const int o3 = k < L.ks ? -1 : (k > L.ke ? 1 : 0);
@@ -103,7 +105,9 @@ extern "C" int pb_halo_exchange_local(const pb_pack_t *pack, const pb_cfg_t *cfg
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   const Lay L(*cfg);
-  const long long n = (long long)L.ncell * pack->nblocks;
+  const Shell sh(L);
+  const long long n = (long long)sh.n * pack->nblocks;
+  if (n <= 0) return PB_OK;
   const int T = 256;
   halo_local_kernel<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(*pack, *cfg, halo_fields(*pack, *cfg, cons));
   return check_launch("halo_local_kernel");

@@ -325,6 +325,30 @@ __global__ void __launch_bounds__(128, 5) update_fused_kernel(const pb_pack_t pa
   }
 }
 
+// Same update with the geometric sources already in gsrc (CalculateFluidSourceTerms ran as its own
+// launch): a pure streaming kernel (24 flux + 4 source + 16 cons words in, 8 out per zone), few registers.
+template <bool MHD>
+__global__ void __launch_bounds__(256, 4) update_stream_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *u0, const Real *ubase,
+                                                               Real beta, Real bdt, Real *uout, const Real *gsrc, Real *dudt_out) {
+  constexpr int NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!interior_zone(L, pack.nblocks, 0, 0, 0, b, k, j, i)) return;
+  const int N = L.ncell, o = L.idx(k, j, i);
+  Real du[NCn];
+  flux_div<NCn>(L, pack.blocks[b], pack.flux + (size_t)b * L.ndim * NCn * N, o, du);
+#pragma unroll
+  for (int l = 0; l < 4; ++l) du[CMOM + l] = 1.0 * du[CMOM + l] + 1.0 * __ldg(gsrc + ((size_t)b * 4 + l) * N + o);
+  const Real w2 = 1.0 - beta;
+#pragma unroll
+  for (int l = 0; l < NCn; ++l) {
+    const size_t a = ((size_t)b * NCn + l) * N + o;
+    const Real uavg = beta * u0[a] + w2 * ubase[a];
+    uout[a] = 1.0 * uavg + bdt * du[l];
+    if (dudt_out) dudt_out[a] = du[l];
+  }
+}
+
 // Ghost zones of the same update: WeightedSumData runs over ENTIRE arrays (update.hpp:77-80) and
 // dUdt is zero outside the interior, so uout = beta*u0 + (1-beta)*ubase there. The values matter
 // only to the stale-prim ApplyFloors of region 7 (which may re-invert a ghost zone and thereby
@@ -424,9 +448,29 @@ extern "C" int pb_weighted_sum(const double *x, const double *y, double w1, doub
   return check_launch("weighted_sum_kernel");
 }
 
+extern "C" int pb_update_from_sources(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *u0, const double *ubase,
+                                      double beta, double bdt, double *uout, const double *gsrc, double *dudt_out,
+                                      int update_ghosts, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!u0 || !ubase || !uout || !gsrc) return set_error(PB_EINVAL, "NULL container");
+  const int T = 256;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd)
+    update_stream_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, gsrc, dudt_out);
+  else
+    update_stream_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, gsrc, dudt_out);
+  if (update_ghosts) {
+    const Lay L(*cfg);
+    const long long ntot = (long long)L.ncell * pack->nblocks;
+    update_ghost_kernel<<<grid_for(ntot, 256), 256, 0, s>>>(*cfg, pack->nblocks, 5 + 3 * cfg->mhd, u0, ubase, beta, uout);
+  }
+  return check_launch("update_stream_kernel");
+}
+
 extern "C" int pb_update_fused(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *u0, const double *ubase,
                                double beta, double bdt, double *uout, double *dudt_out, double *gsrc_out,
-                               void *stream) {
+                               int update_ghosts, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (!u0 || !ubase || !uout) return set_error(PB_EINVAL, "NULL conserved container");
@@ -436,8 +480,10 @@ extern "C" int pb_update_fused(const pb_pack_t *pack, const pb_cfg_t *cfg, const
     update_fused_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, dudt_out, gsrc_out);
   else
     update_fused_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, dudt_out, gsrc_out);
-  const Lay L(*cfg);
-  const long long ntot = (long long)L.ncell * pack->nblocks;
-  update_ghost_kernel<<<grid_for(ntot, 256), 256, 0, s>>>(*cfg, pack->nblocks, 5 + 3 * cfg->mhd, u0, ubase, beta, uout);
+  if (update_ghosts) {
+    const Lay L(*cfg);
+    const long long ntot = (long long)L.ncell * pack->nblocks;
+    update_ghost_kernel<<<grid_for(ntot, 256), 256, 0, s>>>(*cfg, pack->nblocks, 5 + 3 * cfg->mhd, u0, ubase, beta, uout);
+  }
   return check_launch("update_fused_kernel");
 }

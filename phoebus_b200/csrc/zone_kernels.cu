@@ -93,39 +93,167 @@ PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const Point
   return ok;
 }
 
-// ------------------------------------------------------------------ ConToPrim::Solve
-// ref: src/fluid/fluid.cpp:477-517
+// ------------------------------------------------------------------ zone flags
+// One byte per zone (ghosts included) lets the sequencer skip the zones on which the fixup and
+// floor tasks are no-ops (almost all of them) without re-reading their primitives:
+//   ZF_FAIL  the last entire-domain c2p failed here (fail == 0)
+//   ZF_FLOOR floors/ceilings would change the zone's current primitives (post-c2p pass pending)
+//   ZF_STALE floors/ceilings would change the zone's FINAL primitives of the last stage, i.e. the
+//            stale-prim ApplyFloors of the next stage's region 7 fires here
+enum { ZF_FAIL = 1, ZF_FLOOR = 2, ZF_STALE = 4 };
+
+// first part of ApplyFloors (ref: src/fixup/fixup.cpp:370-440): decides whether the floors apply.
 template <bool MHD>
-__global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
-                           unsigned long long *err_count) {
-  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
-  const Lay L(cfg);
-  int b, k, j, i;
-  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
-  const int o = L.idx(k, j, i);
-  const pb_block_t &blk = pack.blocks[b];
-  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
-  PointGeom g;
-  g.load(gt, 0, gt.cell(k, j, i));
-  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
-  const ZonePtr<MHD> z(pack, cons, L, b, o);
-  Real U[NCn], P[NP];
-  load_comps<NCn>(z.cons, L.ncell, U);
-  const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, L.ndim, U, P, err_count);
-  *z.fail = ok ? 1.0 : 0.0;
+PB_DEV bool floors_decide(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const Real *P, Real &drho,
+                          Real &du, Real &sie_floor) {
+  Real rho_floor = 0.0; // ref passes an uninitialised rho_floor; only ExpX1RhoU reads it
+  get_floors(cfg, fc.A, fc.B, fc.x1, fc.x2, fc.x3, rho_floor, sie_floor);
+  const Real e_max = cfg.sie_max;
+  Real rho_floor_max = rho_floor;
+  Real u_floor_max = rho_floor * sie_floor;
+  if (cfg.enable_mhd_floors) {
+    Real Bsq = 0.0, Bdotv = 0.0;
+    const Real vp[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
+    Real bp[3] = {0, 0, 0};
+    if (MHD)
+      for (int a = 0; a < 3; ++a) bp[a] = P[PB_ + a];
+    const Real W = lorentz_factor(vp, g);
+    const Real iW = 1.0 / W;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        Bsq += g.g4(a + 1, c + 1) * bp[a] * bp[c];
+        Bdotv += g.g4(a + 1, c + 1) * bp[a] * vp[c]; // vp, not vp/W: ref fixup.cpp:420-425
+      }
+    const Real bcon0 = W * Bdotv / g.alpha;
+    const Real bsq = (Bsq + g.alpha * g.alpha * bcon0 * bcon0) * iW * iW;
+    rho_floor_max = dmax(rho_floor_max, bsq / cfg.bsqorho_max);
+    u_floor_max = dmax(u_floor_max, bsq / cfg.bsqou_max);
+    rho_floor_max = dmax(rho_floor_max, dmax(P[PENG], u_floor_max) / e_max);
+  }
+  drho = rho_floor_max - P[PRHO];
+  du = u_floor_max - P[PENG];
+  return (drho > 0. || du > 0.);
+}
+// ceiling test of ApplyFloors (ref: fixup.cpp:505-507) on the given primitives
+PB_DEV bool ceiling_decide(const pb_cfg_t &cfg, const PointGeom &g, const Real *P, Real &W) {
+  const Real vpcon[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
+  W = lorentz_factor(vpcon, g);
+  return (W > cfg.gam_max || P[PENG] / P[PRHO] > cfg.sie_max);
+}
+// would ApplyFloors change this zone?
+template <bool MHD> PB_DEV bool floors_needed(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const Real *P) {
+  Real drho, du, sf, W;
+  if (floors_decide<MHD>(cfg, fc, g, P, drho, du, sf)) return true;
+  return ceiling_decide(cfg, g, P, W);
 }
 
-// ------------------------------------------------------------------ ConToPrim::Solve fixup
-// ref: src/fixup/fixup_c2p.cpp:170-353
+// Conserved variables of a zone as ApplyFloors sees them. In the stale-prim pass of region 7 the
+// ghost zones of the stage-output container hold beta*u0 + (1-beta)*ubase (WeightedSumData runs over
+// entire arrays and dUdt is zero there); the sequencer does not materialise that, it is formed here.
+struct LazyGhost {
+  const Real *u0, *ubase; // NULL: read the container
+  Real beta;
+};
+
+// ApplyFloors on one zone, ref: src/fixup/fixup.cpp:370-684 (fluid part). Returns true if the zone
+// was changed.
 template <bool MHD>
-__global__ void __launch_bounds__(128, 4) c2p_fixup_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg) {
+PB_DEV bool floors_zone(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const ZonePtr<MHD> &z, int ndim,
+                        const Real *lazy_u0, const Real *lazy_ubase, Real beta, unsigned long long *counters) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons, prs = NC<MHD>::prs, gm1 = NC<MHD>::gm1;
+  const int N = z.ncell;
+  const Eos eos(cfg);
+  Real P[NP];
+  load_comps<NP>(z.prim, N, P);
+  Real bp[3] = {0, 0, 0};
+  if (MHD)
+    for (int a = 0; a < 3; ++a) bp[a] = P[PB_ + a];
+  Real drho, du, sie_floor;
+  bool floor_applied = floors_decide<MHD>(cfg, fc, g, P, drho, du, sie_floor), ceiling_applied = false;
+  if (floor_applied) {
+    drho = dmax(drho, du / sie_floor);
+    du = dmax(du, sie_floor * drho);
+  }
+  Real U[NCn];
+  bool have_U = false, store_P = false, store_U = false;
+  auto load_U = [&]() {
+    if (lazy_u0) {
+      const Real w2 = 1.0 - beta;
+#pragma unroll
+      for (int n = 0; n < NCn; ++n) U[n] = 1.0 * (beta * lazy_u0[(size_t)n * N] + w2 * lazy_ubase[(size_t)n * N]) + 0.0;
+    } else {
+      load_comps<NCn>(z.cons, N, U);
+    }
+    have_U = true;
+  };
+  Real temp_out = 0.0;
+  if (floor_applied) {
+    if (counters) atomicAdd(&counters[0], 1ULL);
+    load_U();
+    const Real vp_normalobs[3] = {0, 0, 0};
+    const Real dprs = eos.P_rho_sie(drho, ratio(du, drho));
+    const Real dgm1 = ratio(eos.K_rho_sie(drho, ratio(du, drho)), dprs);
+    Real dcrho, dS[3], dBcons[3], dtau, nosig[3];
+    p2c<false>(drho, vp_normalobs, bp, du, dprs, dgm1, g, dcrho, dS, dBcons, dtau, nosig);
+    U[CRHO] += dcrho;
+    for (int a = 0; a < 3; ++a) U[CMOM + a] += dS[a];
+    U[CENG] += dtau;
+    // the in-kernel c2p reads the updated cons and writes prims/temp/mu/csig/cons itself
+#pragma unroll
+    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * N] = U[n];
+    Real Pn[NP];
+    const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, ndim, U, Pn, nullptr);
+    // refresh the local view of the zone from what c2p wrote (it never touches c.bfield)
+    load_comps<NP>(z.prim, N, P);
+    load_comps<5>(z.cons, N, U);
+    if (!ok) {
+      if (counters) atomicAdd(&counters[2], 1ULL);
+      P[PRHO] = drho;
+      for (int a = 0; a < 3; ++a) P[PVEL + a] = vp_normalobs[a];
+      P[PENG] = du;
+      temp_out = eos.T_rho_sie(P[PRHO], P[PENG] / P[PRHO]);
+      *z.temp = temp_out;
+      p2c<false>(drho, vp_normalobs, bp, du, dprs, dgm1, g, U[CRHO], dS, dBcons, U[CENG], nosig);
+      for (int a = 0; a < 3; ++a) U[CMOM + a] = dS[a];
+      store_P = store_U = true;
+    }
+    // bp keeps the pre-c2p p.bfield, as in the reference (fixup.cpp:441-447)
+  }
+  Real W;
+  ceiling_applied = ceiling_decide(cfg, g, P, W);
+  if (ceiling_applied) {
+    if (counters) atomicAdd(&counters[1], 1ULL);
+    if (!have_U) load_U();
+    Real vpcon[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
+    const Real rescale = sqrt(cfg.gam_max * cfg.gam_max - 1.) / (W * W - 1.); // sic, ref: fixup.cpp:510
+    for (int a = 0; a < 3; ++a) vpcon[a] *= rescale;
+    for (int a = 0; a < 3; ++a) P[PVEL + a] = vpcon[a];
+    Real dS[3], dBcons[3], nosig[3];
+    p2c<false>(P[PRHO], vpcon, bp, P[PENG], P[prs], P[gm1], g, U[CRHO], dS, dBcons, U[CENG], nosig);
+    for (int a = 0; a < 3; ++a) U[CMOM + a] = dS[a];
+    store_P = store_U = true;
+  }
+  if (floor_applied || ceiling_applied) {
+    temp_out = eos.T_rho_sie(P[PRHO], ratio(P[PENG], P[PRHO]));
+    P[prs] = eos.P_rho_T(P[PRHO], temp_out);
+    P[gm1] = ratio(eos.K_rho_T(P[PRHO], temp_out), P[prs]);
+    *z.temp = temp_out;
+    store_P = true;
+  }
+  if (store_P) store_comps<NP>(z.prim, N, P);
+  if (store_U) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * N] = U[n];
+  }
+  return floor_applied || ceiling_applied;
+}
+
+// ConservedToPrimitiveFixup on one failed zone, ref: src/fixup/fixup_c2p.cpp:170-353
+template <bool MHD>
+PB_DEV void fixup_zone(const pb_cfg_t &cfg, const Lay &L, const PointGeom &g, const ZonePtr<MHD> &z) {
   constexpr int NP = NC<MHD>::nprim, prs = NC<MHD>::prs, gm1 = NC<MHD>::gm1;
-  const Lay L(cfg);
-  int b, k, j, i;
-  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
-  const int o = L.idx(k, j, i);
-  const ZonePtr<MHD> z(pack, cons, L, b, o);
-  if (*z.fail != 0.0) return;
   const int N = L.ncell;
   const int st1 = L.ni, st2 = L.ni * L.nj;
   const Real *fl = z.fail;
@@ -157,10 +285,6 @@ __global__ void __launch_bounds__(128, 4) c2p_fixup_kernel(const pb_pack_t pack,
     P[PENG] = 100. * R_SMALL;
     for (int ii = 0; ii < 3; ++ii) P[PVEL + ii] = 0.;
   }
-  const pb_block_t &blk = pack.blocks[b];
-  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
-  PointGeom g;
-  g.load(gt, 0, gt.cell(k, j, i));
   Real vpcon[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
   Real W = lorentz_factor(vpcon, g);
   if (W > gamma_max) {
@@ -184,130 +308,142 @@ __global__ void __launch_bounds__(128, 4) c2p_fixup_kernel(const pb_pack_t pack,
   for (int a = 0; a < L.ndim; ++a) z.csig[(size_t)a * N] = sig[a];
 }
 
-// ------------------------------------------------------------------ ApplyFloors
-// ref: src/fixup/fixup.cpp:370-684 (fluid part)
+struct ZoneCtx { // everything a zone task needs, built from the thread's (b,k,j,i)
+  int b, k, j, i, o;
+  bool interior;
+};
+
+// ------------------------------------------------------------------ ConToPrim::Solve
+// ref: src/fluid/fluid.cpp:477-517. With zflags != NULL the kernel also records, per zone, whether
+// the c2p failed and whether ApplyFloors will have to touch the zone (one extra byte written instead
+// of a second full pass over the primitives).
 template <bool MHD>
-__global__ void __launch_bounds__(128, 5) floors_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
-                              unsigned long long *counters) {
-  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons, prs = NC<MHD>::prs, gm1 = NC<MHD>::gm1;
+__global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                                                     unsigned long long *err_count, unsigned char *zflags) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   const Lay L(cfg);
   int b, k, j, i;
   if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
   const int o = L.idx(k, j, i);
-  const int N = L.ncell;
   const pb_block_t &blk = pack.blocks[b];
-  const ZonePtr<MHD> z(pack, cons, L, b, o);
-  const Eos eos(cfg);
-  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
-  Real rho_floor = 0.0, sie_floor; // ref passes an uninitialised rho_floor; only ExpX1RhoU reads it
-  get_floors(cfg, fc.A, fc.B, fc.x1, fc.x2, fc.x3, rho_floor, sie_floor);
-  const Real gamma_max = cfg.gam_max, e_max = cfg.sie_max;
-  const Real bsqorho_max = cfg.bsqorho_max, bsqou_max = cfg.bsqou_max;
-  Real rho_floor_max = rho_floor;
-  Real u_floor_max = rho_floor * sie_floor;
-  bool floor_applied = false, ceiling_applied = false;
   const GeomTab gt(cfg, pack.geom, blk.geom_slot);
   PointGeom g;
   g.load(gt, 0, gt.cell(k, j, i));
-  const Real alpha = g.alpha;
-  Real P[NP];
-  load_comps<NP>(z.prim, N, P);
-  Real bp[3] = {0, 0, 0};
-  if (MHD)
-    for (int a = 0; a < 3; ++a) bp[a] = P[PB_ + a];
-  if (cfg.enable_mhd_floors) {
-    Real Bsq = 0.0, Bdotv = 0.0;
-    const Real vp[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
-    const Real W = lorentz_factor(vp, g);
-    const Real iW = 1.0 / W;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        Bsq += g.g4(a + 1, c + 1) * bp[a] * bp[c];
-        Bdotv += g.g4(a + 1, c + 1) * bp[a] * vp[c]; // vp, not vp/W: ref fixup.cpp:420-425
-      }
-    const Real bcon0 = W * Bdotv / alpha;
-    const Real bsq = (Bsq + alpha * alpha * bcon0 * bcon0) * iW * iW;
-    rho_floor_max = dmax(rho_floor_max, bsq / bsqorho_max);
-    u_floor_max = dmax(u_floor_max, bsq / bsqou_max);
-    rho_floor_max = dmax(rho_floor_max, dmax(P[PENG], u_floor_max) / e_max);
-  }
-  Real drho = rho_floor_max - P[PRHO];
-  Real du = u_floor_max - P[PENG];
-  if (drho > 0. || du > 0.) {
-    floor_applied = true;
-    drho = dmax(drho, du / sie_floor);
-    du = dmax(du, sie_floor * drho);
-  }
-  Real U[NCn];
-  bool have_U = false, store_P = false, store_U = false;
-  Real temp_out = 0.0;
-  if (floor_applied) {
-    if (counters) atomicAdd(&counters[0], 1ULL);
-    load_comps<NCn>(z.cons, N, U);
-    have_U = true;
-    const Real vp_normalobs[3] = {0, 0, 0};
-    const Real dprs = eos.P_rho_sie(drho, ratio(du, drho));
-    const Real dgm1 = ratio(eos.K_rho_sie(drho, ratio(du, drho)), dprs);
-    Real dcrho, dS[3], dBcons[3], dtau, nosig[3];
-    p2c<false>(drho, vp_normalobs, bp, du, dprs, dgm1, g, dcrho, dS, dBcons, dtau, nosig);
-    U[CRHO] += dcrho;
-    for (int a = 0; a < 3; ++a) U[CMOM + a] += dS[a];
-    U[CENG] += dtau;
-    // the in-kernel c2p reads the updated cons and writes prims/temp/mu/csig/cons itself
-#pragma unroll
-    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * N] = U[n];
-    Real Pn[NP];
-    load_comps<NP>(z.prim, N, Pn);
-    const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
-    const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, L.ndim, U, Pn, nullptr);
-    // refresh the local view of the zone from what c2p wrote
-    load_comps<NP>(z.prim, N, P);
-    load_comps<NCn>(z.cons, N, U);
-    (void)nan_in;
-    if (!ok) {
-      if (counters) atomicAdd(&counters[2], 1ULL);
-      P[PRHO] = drho;
-      for (int a = 0; a < 3; ++a) P[PVEL + a] = vp_normalobs[a];
-      P[PENG] = du;
-      temp_out = eos.T_rho_sie(P[PRHO], P[PENG] / P[PRHO]);
-      *z.temp = temp_out;
-      p2c<false>(drho, vp_normalobs, bp, du, dprs, dgm1, g, U[CRHO], dS, dBcons, U[CENG], nosig);
-      for (int a = 0; a < 3; ++a) U[CMOM + a] = dS[a];
-      store_P = store_U = true;
+  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  Real U[NCn], P[NP];
+  load_comps<NCn>(z.cons, L.ncell, U);
+  const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, L.ndim, U, P, err_count);
+  *z.fail = ok ? 1.0 : 0.0;
+  if (zflags) {
+    unsigned char f = ok ? 0 : ZF_FAIL;
+    if (cfg.enable_floors) {
+      // the primitives ApplyFloors will see: what c2p just wrote, or (NaN guard / unbracketed root)
+      // whatever the zone held before
+      const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
+      if (!ok) load_comps<NP>(z.prim, L.ncell, P);
+      (void)nan_in;
+      if (floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_FLOOR;
     }
-    // bp keeps the pre-c2p p.bfield, as in the reference (fixup.cpp:441-447)
+    zflags[(size_t)b * L.ncell + o] = f;
   }
-  Real vpcon[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
-  const Real W = lorentz_factor(vpcon, g);
-  if (W > gamma_max || P[PENG] / P[PRHO] > e_max) ceiling_applied = true;
-  if (ceiling_applied) {
-    if (counters) atomicAdd(&counters[1], 1ULL);
-    if (!have_U) {
-      load_comps<NCn>(z.cons, N, U);
-      have_U = true;
-    }
-    const Real rescale = sqrt(gamma_max * gamma_max - 1.) / (W * W - 1.); // sic, ref: fixup.cpp:510
-    for (int a = 0; a < 3; ++a) vpcon[a] *= rescale;
-    for (int a = 0; a < 3; ++a) P[PVEL + a] = vpcon[a];
-    Real dS[3], dBcons[3], nosig[3];
-    p2c<false>(P[PRHO], vpcon, bp, P[PENG], P[prs], P[gm1], g, U[CRHO], dS, dBcons, U[CENG], nosig);
-    for (int a = 0; a < 3; ++a) U[CMOM + a] = dS[a];
-    store_P = store_U = true;
+}
+
+// ------------------------------------------------------------------ ConToPrim::Solve fixup
+// MODE 0: the task as the reference runs it (every interior zone reads its fail flag).
+// MODE 1 / 2: driven by the zone flags (post-c2p pass / stale-prim pass of region 7); the zone's
+// floor flag is refreshed because the fixup rewrites its primitives.
+template <bool MHD, int MODE>
+__global__ void __launch_bounds__(128, 4) c2p_fixup_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                                                           unsigned char *zflags) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  if (MODE != 0) {
+    if (!(zflags[(size_t)b * L.ncell + o] & ZF_FAIL)) return;
   }
-  if (floor_applied || ceiling_applied) {
-    temp_out = eos.T_rho_sie(P[PRHO], ratio(P[PENG], P[PRHO]));
-    P[prs] = eos.P_rho_T(P[PRHO], temp_out);
-    P[gm1] = ratio(eos.K_rho_T(P[PRHO], temp_out), P[prs]);
-    *z.temp = temp_out;
-    store_P = true;
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  if (MODE == 0 && *z.fail != 0.0) return;
+  const pb_block_t &blk = pack.blocks[b];
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  fixup_zone<MHD>(cfg, L, g, z);
+  if (MODE != 0 && cfg.enable_floors) {
+    constexpr int NP = NC<MHD>::nprim;
+    Real P[NP];
+    load_comps<NP>(z.prim, L.ncell, P);
+    const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+    const bool need = floors_needed<MHD>(cfg, fc, g, P);
+    unsigned char f = zflags[(size_t)b * L.ncell + o];
+    const unsigned char bit = MODE == 1 ? ZF_FLOOR : ZF_STALE;
+    f = need ? (f | bit) : (f & ~bit);
+    zflags[(size_t)b * L.ncell + o] = f;
   }
-  if (store_P) store_comps<NP>(z.prim, N, P);
-  if (store_U) {
-#pragma unroll
-    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * N] = U[n];
+}
+
+// ------------------------------------------------------------------ ApplyFloors
+// MODE 0: full scan (the task as the reference runs it). MODE 1: zones flagged ZF_FLOOR after the
+// entire-domain c2p; leaves ZF_STALE = "floors would fire again on the final primitives".
+// MODE 2: zones flagged ZF_STALE (region 7, stale primitives), ghost cons formed lazily.
+template <bool MHD, int MODE>
+__global__ void __launch_bounds__(128, 4) floors_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                                                        unsigned long long *counters, unsigned char *zflags, const LazyGhost lazy) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  unsigned char f = 0;
+  if (MODE != 0) {
+    f = zflags[(size_t)b * L.ncell + o];
+    if (!(f & (MODE == 1 ? ZF_FLOOR : ZF_STALE))) return;
   }
+  const pb_block_t &blk = pack.blocks[b];
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  const bool ghost = !(i >= L.is && i <= L.ie && j >= L.js && j <= L.je && k >= L.ks && k <= L.ke);
+  const Real *l0 = nullptr, *lb = nullptr;
+  if (MODE == 2 && ghost && lazy.u0) {
+    l0 = lazy.u0 + (size_t)b * NCn * L.ncell + o;
+    lb = lazy.ubase + (size_t)b * NCn * L.ncell + o;
+  }
+  floors_zone<MHD>(cfg, fc, g, z, L.ndim, l0, lb, lazy.beta, counters);
+  if (MODE == 1) {
+    Real P[NP];
+    load_comps<NP>(z.prim, L.ncell, P);
+    f &= ~(ZF_FLOOR | ZF_STALE);
+    if (floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_STALE;
+    zflags[(size_t)b * L.ncell + o] = f;
+  }
+}
+
+// (Re)build the zone flags from the current primitives and fail field: needed once before the first
+// flag-driven stage and whenever something outside the sequencer has changed p.* or fail.
+template <bool MHD>
+__global__ void __launch_bounds__(128, 4) flags_scan_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Region reg,
+                                                            unsigned char *zflags) {
+  constexpr int NP = NC<MHD>::nprim;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  const pb_block_t &blk = pack.blocks[b];
+  unsigned char f = pack.fail[(size_t)b * L.ncell + o] == 0.0 ? ZF_FAIL : 0;
+  if (cfg.enable_floors) {
+    const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+    const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+    PointGeom g;
+    g.load(gt, 0, gt.cell(k, j, i));
+    Real P[NP];
+    load_comps<NP>(pack.prim + (size_t)b * NP * L.ncell + o, L.ncell, P);
+    if (floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_STALE;
+  }
+  zflags[(size_t)b * L.ncell + o] = f;
 }
 
 // ------------------------------------------------------------------ PrimToCons
@@ -354,12 +490,17 @@ __global__ void p2c_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons,
 // reference's order x1, x2, x3), which makes the fill race-free and single-launch. The conversion
 // (inflow check, p2c of the prim-filled ghosts) is pointwise and follows in the same thread.
 template <bool MHD>
-__global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
-                          unsigned long long *err_count) {
+__global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const int nlist,
+                                                    unsigned long long *err_count) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   const Lay L(cfg);
-  int b, k, j, i;
-  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const Shell sh(L);
+  // threads enumerate the ghost shell of the blocks that touch a mesh boundary
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)sh.n * nlist) return;
+  const int b = pack.bc_blocks ? pack.bc_blocks[t / sh.n] : (int)(t / sh.n);
+  int k, j, i;
+  sh.cell(L, (int)(t % sh.n), k, j, i);
   const pb_block_t &blk = pack.blocks[b];
   const int lo[3] = {L.is, L.js, L.ks}, hi[3] = {L.ie, L.je, L.ke};
   const int idx[3] = {i, j, k};
@@ -527,48 +668,85 @@ unsigned long long *err_counter() {
 
 using namespace pb;
 
-extern "C" int pb_cons_to_prim(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
-                               const int jb[2], const int kb[2], void *stream) {
-  int rc = check_args(pack, cfg);
-  if (rc) return rc;
-  if (!cons) return set_error(PB_EINVAL, "cons is NULL");
+namespace pb {
+// sequencer-internal launchers (abi_common.cu)
+int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2], const int jb[2], const int kb[2],
+               unsigned char *zflags, cudaStream_t s) {
   const Region reg{ib[0], ib[1], jb[0], jb[1], kb[0], kb[1]};
   if (reg.n() <= 0) return PB_OK;
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (cfg->mhd) c2p_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter());
-  else c2p_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter());
+  if (cfg->mhd) c2p_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
+  else c2p_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
   return check_launch("c2p_kernel");
 }
-
-extern "C" int pb_c2p_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {
-  int rc = check_args(pack, cfg);
-  if (rc) return rc;
+int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int mode, unsigned char *zflags, cudaStream_t s) {
   if (!cfg->enable_c2p_fixup) return PB_OK; // ref: fixup_c2p.cpp:60-62
   const Lay L(*cfg);
   const Region reg = interior(L);
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
-  cudaStream_t s = (cudaStream_t)stream;
-  if (cfg->mhd) c2p_fixup_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg);
-  else c2p_fixup_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg);
+#define PB_FIX(M, MODE) c2p_fixup_kernel<M, MODE><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, zflags)
+  if (cfg->mhd) {
+    if (mode == 0) PB_FIX(true, 0); else if (mode == 1) PB_FIX(true, 1); else PB_FIX(true, 2);
+  } else {
+    if (mode == 0) PB_FIX(false, 0); else if (mode == 1) PB_FIX(false, 1); else PB_FIX(false, 2);
+  }
+#undef PB_FIX
   return check_launch("c2p_fixup_kernel");
+}
+int launch_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, unsigned long long *counters, int mode,
+                  unsigned char *zflags, const double *lazy_u0, const double *lazy_ubase, double beta, cudaStream_t s) {
+  if (!cfg->enable_floors) return PB_OK; // ref: fixup.cpp:293-295
+  const Lay L(*cfg);
+  const Region reg = entire(L);
+  const int T = zone_threads();
+  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  const LazyGhost lazy{lazy_u0, lazy_ubase, beta};
+#define PB_FLR(M, MODE) floors_kernel<M, MODE><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, counters, zflags, lazy)
+  if (cfg->mhd) {
+    if (mode == 0) PB_FLR(true, 0); else if (mode == 1) PB_FLR(true, 1); else PB_FLR(true, 2);
+  } else {
+    if (mode == 0) PB_FLR(false, 0); else if (mode == 1) PB_FLR(false, 1); else PB_FLR(false, 2);
+  }
+#undef PB_FLR
+  return check_launch("floors_kernel");
+}
+} // namespace pb
+
+extern "C" int pb_cons_to_prim(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
+                               const int jb[2], const int kb[2], void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cons) return set_error(PB_EINVAL, "cons is NULL");
+  return launch_c2p(pack, cfg, cons, ib, jb, kb, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int pb_c2p_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  return launch_fixup(pack, cfg, cons, 0, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int pb_apply_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons,
                                unsigned long long *counters, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
-  if (!cfg->enable_floors) return PB_OK; // ref: fixup.cpp:293-295
+  return launch_floors(pack, cfg, cons, counters, 0, nullptr, nullptr, nullptr, 1.0, (cudaStream_t)stream);
+}
+
+extern "C" int pb_scan_zone_flags(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!pack->zflags) return set_error(PB_EINVAL, "pack has no zflags array");
   const Lay L(*cfg);
   const Region reg = entire(L);
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
   cudaStream_t s = (cudaStream_t)stream;
-  if (cfg->mhd) floors_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, counters);
-  else floors_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, counters);
-  return check_launch("floors_kernel");
+  if (cfg->mhd) flags_scan_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, reg, pack->zflags);
+  else flags_scan_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, reg, pack->zflags);
+  return check_launch("flags_scan_kernel");
 }
 
 extern "C" int pb_prim_to_cons(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2],
@@ -589,12 +767,14 @@ extern "C" int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   const Lay L(*cfg);
-  const Region reg = entire(L);
+  const Shell sh(L);
+  const int nlist = pack->bc_blocks ? pack->n_bc_blocks : pack->nblocks;
+  if (nlist <= 0 || sh.n <= 0) return PB_OK;
   const int T = zone_threads();
-  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  const unsigned grid = grid_for((long long)sh.n * nlist, T);
   cudaStream_t s = (cudaStream_t)stream;
-  if (cfg->mhd) bc_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter());
-  else bc_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter());
+  if (cfg->mhd) bc_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, nlist, err_counter());
+  else bc_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, nlist, err_counter());
   return check_launch("bc_kernel");
 }
 

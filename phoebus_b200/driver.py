@@ -73,6 +73,15 @@ class FluidDriver:
             _lib.check(L.pb_halo_unpack(pk, cfg, cons.data_ptr(), h["rplan"].data_ptr(), h["nrecv"], h["rbuf"].data_ptr(), s),
                        "pb_halo_unpack")
 
+    def ensure_flags(self):
+        """zone flags must describe the current p.* / fail fields before a flag-driven stage"""
+        m = self.m
+        if m.zflags is not None and not m.flags_valid:
+            pk, cfg = self._pk()
+            _lib.check(self.L.pb_scan_zone_flags(pk, cfg, self._stream()), "pb_scan_zone_flags")
+            m.flags_valid = True
+            self.launches += 1
+
     def stage(self, stage, dt):
         m, L = self.m, self.L
         pk, cfg = self._pk()
@@ -81,23 +90,34 @@ class FluidDriver:
         sc0, sc1 = m.cons[self.names[stage - 1]], m.cons[self.names[stage]]
         base = m.cons["base"]
         cnt = C.c_void_p(m.counters.data_ptr())
-        if self.timers is not None:
-            return self._stage_timed(stage, dt)
+        self.ensure_flags()
         if self.dist is None:
             _lib.check(L.pb_rk_stage(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s), "pb_rk_stage")
         else:
             _lib.check(L.pb_rk_stage_pre(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s),
                        "pb_rk_stage_pre")
-            self.exchange(sc1)
+            if self.timers is not None:
+                t = self.torch
+                e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+                e0.record()
+                self.exchange(sc1)
+                e1.record()
+                self.timers.setdefault("halo", []).append((e0, e1))
+            else:
+                self.exchange(sc1)
             _lib.check(L.pb_rk_stage_post(pk, cfg, sc1.data_ptr(), cnt, s), "pb_rk_stage_post")
         self.launches += self.LAUNCHES_PER_STAGE
 
-    # kernels launched per stage by pb_rk_stage: flux x ndim, emf + ct, fix, update + ghosts,
-    # fixup, floors, halo, bcs, c2p, fixup, floors
+    # kernels launched per stage by pb_rk_stage: flux x ndim, emf + ct, fix, [source,] update
+    # [+ ghosts], fixup, floors, halo, bcs, c2p, fixup, floors
     @property
     def LAUNCHES_PER_STAGE(self):
         m = self.m
-        n = m.ndim + 2 + 1 + 1 + 1
+        n = m.ndim + 1 + 1 + 1 + 1
+        if m.gsrc is not None:
+            n += 1
+        if m.zflags is None:
+            n += 1
         if m.p.mhd and m.ndim > 1:
             n += 2
         if m.p.enable_flux_fixup:
@@ -106,47 +126,25 @@ class FluidDriver:
             n += 2
         if m.p.enable_floors:
             n += 2
+        if self.dist is not None:
+            n += 2 * len(self.halo)
         return n
 
-    def _stage_timed(self, stage, dt):
-        """Same task order as pb_rk_stage, one C-ABI call per task, CUDA events around each task
-        group on the launching stream (bench.py's per-kernel durations)."""
-        m, L = self.m, self.L
-        pk, cfg = self._pk()
-        s = self._stream()
-        t = self.torch
-        beta = self.betas[stage - 1]
-        sc0, sc1 = m.cons[self.names[stage - 1]], m.cons[self.names[stage]]
-        base = m.cons["base"]
-        cnt = C.c_void_p(m.counters.data_ptr())
-
-        def timed(name, fn):
-            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            self.timers.setdefault(name, []).append((e0, e1))
-        I2 = C.c_int * 2
-        ib, jb, kb = I2(0, m.ni - 1), I2(0, m.nj - 1), I2(0, m.nk - 1)
-        timed("flux", lambda: _lib.check(L.pb_calculate_fluxes(pk, cfg, s), "pb_calculate_fluxes"))
-        timed("ct_fix", lambda: (_lib.check(L.pb_flux_ct(pk, cfg, s), "pb_flux_ct"),
-                                 _lib.check(L.pb_fix_fluxes(pk, cfg, s), "pb_fix_fluxes")))
-        timed("update", lambda: _lib.check(L.pb_update_fused(pk, cfg, sc0.data_ptr(), base.data_ptr(), beta, beta * dt,
-                                                             sc1.data_ptr(), None, None, s), "pb_update_fused"))
-        timed("stale_fixup_floors", lambda: (_lib.check(L.pb_c2p_fixup(pk, cfg, sc1.data_ptr(), s), "pb_c2p_fixup"),
-                                             _lib.check(L.pb_apply_floors(pk, cfg, sc1.data_ptr(), cnt, s), "pb_apply_floors")))
-        timed("halo", lambda: self.exchange(sc1))
-        timed("bcs", lambda: _lib.check(L.pb_apply_bcs(pk, cfg, sc1.data_ptr(), s), "pb_apply_bcs"))
-        timed("c2p", lambda: _lib.check(L.pb_cons_to_prim(pk, cfg, sc1.data_ptr(), ib, jb, kb, s), "pb_cons_to_prim"))
-        timed("fixup_floors", lambda: (_lib.check(L.pb_c2p_fixup(pk, cfg, sc1.data_ptr(), s), "pb_c2p_fixup"),
-                                       _lib.check(L.pb_apply_floors(pk, cfg, sc1.data_ptr(), cnt, s), "pb_apply_floors")))
-        self.launches += self.LAUNCHES_PER_STAGE
+    def enable_profile(self, on=True):
+        """per-task CUDA-event timing inside the C-ABI sequencer (pb_profile_enable)"""
+        self.L.pb_profile_enable(int(on))
+        self.timers = {} if on else None
 
     def timer_summary(self):
-        """name -> (calls, total ms); call after a synchronize"""
-        out = {}
+        """task -> (calls, total ms) since the last call; synchronises the recorded events"""
+        ms = (C.c_double * len(_lib.TASK_NAMES))()
+        calls = (C.c_int * len(_lib.TASK_NAMES))()
+        self.L.pb_profile_read(ms, calls)
+        out = {n: (calls[i], ms[i]) for i, n in enumerate(_lib.TASK_NAMES) if calls[i]}
         for name, evs in (self.timers or {}).items():
             out[name] = (len(evs), sum(e0.elapsed_time(e1) for e0, e1 in evs))
+        if self.timers is not None:
+            self.timers = {}
         return out
 
     def estimate_dt(self):

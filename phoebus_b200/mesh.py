@@ -54,12 +54,13 @@ def rank_grid(world, nblk, ndim):
 
 class MeshPack:
     def __init__(self, params, device=None, rank=0, world=1, mesh_xmin=None, mesh_xmax=None, geom_par=None,
-                 alloc_fields=True):
+                 alloc_fields=True, use_zflags=True, use_gsrc=True):
         import torch
         self.torch = torch
         self.p = params
         self.rank, self.world = rank, world
         self.device = device
+        self.use_zflags, self.use_gsrc = use_zflags, use_gsrc
         p = params
         self.ndim, self.ng = p.ndim, p.ng
         self.nx = tuple(p.block_nx)
@@ -236,6 +237,10 @@ class MeshPack:
         for f in range(6):
             self.blocks_host[n].bc[f] = bc[f]
 
+    def invalidate_flags(self):
+        """call after writing p.* or fail from outside the sequencer (pgens, state loads)"""
+        self.flags_valid = False
+
     # ------------------------------------------------------------------ device memory
     def _alloc(self):
         t = self.torch
@@ -248,6 +253,10 @@ class MeshPack:
         self.flux = z(self.ndim, self.ncons)
         self.emf = z(3)
         self.cons = {"base": z(self.ncons), "1": z(self.ncons)}
+        # accelerators of the sequencer (include/phoebus_b200.h): zone flags, sources container
+        self.zflags = t.zeros((nb,) + self.shape, dtype=t.uint8, device=dev) if self.use_zflags else None
+        self.gsrc = z(4) if self.use_gsrc else None
+        self.flags_valid = False
         self.counters = t.zeros(3, dtype=t.int64, device=dev)
         self.dt_dev = t.zeros(1, dtype=t.float64, device=dev)
         self._upload_meta()
@@ -258,6 +267,9 @@ class MeshPack:
         self.blocks_dev = t.from_numpy(raw).to(self.device)
         self.geom = t.from_numpy(self.geom_host).to(self.device)
         self.floor_tab = t.from_numpy(self.floor_host).to(self.device)
+        bcb = [n for n in range(self.nblocks) if any(self.blocks_host[n].bc[f] != 0 for f in range(2 * self.ndim))]
+        self.bc_blocks = t.tensor(bcb if bcb else [0], dtype=t.int32, device=self.device)
+        self.n_bc_blocks = len(bcb)
         pk = PbPack()
         pk.nblocks = self.nblocks
         pk.blocks = self.blocks_dev.data_ptr()
@@ -265,7 +277,12 @@ class MeshPack:
         pk.floor_tab = self.floor_tab.data_ptr()
         for name in ("prim", "temp", "c2p_mu", "fail", "csig", "fsig", "flux", "emf"):
             setattr(pk, name, getattr(self, name).data_ptr())
+        pk.zflags = self.zflags.data_ptr() if self.zflags is not None else None
+        pk.gsrc = self.gsrc.data_ptr() if self.gsrc is not None else None
+        pk.bc_blocks = self.bc_blocks.data_ptr()
+        pk.n_bc_blocks = self.n_bc_blocks
         self.pack = pk
+        self.flags_valid = False
 
     def zones(self):
         """interior zones owned by this pack"""
@@ -273,8 +290,11 @@ class MeshPack:
 
     def bytes_allocated(self):
         n = 0
-        for name in ("prim", "temp", "c2p_mu", "fail", "csig", "fsig", "flux", "emf", "geom", "floor_tab"):
-            n += getattr(self, name).numel() * 8
+        for name in ("prim", "temp", "c2p_mu", "fail", "csig", "fsig", "flux", "emf", "geom", "floor_tab", "gsrc"):
+            if getattr(self, name) is not None:
+                n += getattr(self, name).numel() * 8
+        if self.zflags is not None:
+            n += self.zflags.numel()
         return n + sum(c.numel() * 8 for c in self.cons.values())
 
     # ------------------------------------------------------------------ cell-centre coordinates (pgens)

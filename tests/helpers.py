@@ -53,10 +53,10 @@ def block_lx(p_or_mesh, man, mb, ndim, ng, nx):
     return tuple(lx)
 
 
-def product_mesh(g, device=None, alloc_fields=True):
+def product_mesh(g, device=None, alloc_fields=True, **kw):
     from phoebus_b200.mesh import MeshPack
     fp = product_params(g)
-    mesh = MeshPack(fp, device=device, alloc_fields=alloc_fields)
+    mesh = MeshPack(fp, device=device, alloc_fields=alloc_fields, **kw)
     return mesh, fp
 
 
@@ -84,4 +84,5 @@ def load_product_state(mesh, g, tag="init"):
         for cont in ("base", "1"):
             if get(gid, cont, "c.density") is not None:
                 mesh.cons[cont][n].copy_(torch.from_numpy(fd.stack(get, gid, cont, fd.CONS_FIELDS, shape)))
+    mesh.invalidate_flags()
     return order

@@ -33,19 +33,25 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
-def _setup(name):
+def _setup(name, **kw):
     from phoebus_b200.driver import FluidDriver
     g, p = load_case(name)
-    mesh, fp = product_mesh(g, device=_dev())
+    mesh, fp = product_mesh(g, device=_dev(), **kw)
     order = load_product_state(mesh, g, "init")
     drv = FluidDriver(mesh)
     drv.has_face_speeds = True
     return g, p, mesh, drv, order
 
 
+# the sequencer with and without its accelerators (zone flags, separate source launch) must give
+# the same bits: "exhaustive" runs every task over every zone exactly like the reference
+MODES = {"flagged": dict(use_zflags=True, use_gsrc=True), "exhaustive": dict(use_zflags=False, use_gsrc=False)}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("name", CASES)
-def test_stages_match_reference_dumps(name):
-    g, p, mesh, drv, order = _setup(name)
+def test_stages_match_reference_dumps(name, mode):
+    g, p, mesh, drv, order = _setup(name, **MODES[mode])
     for tag in stage_tags(g):
         man = g.manifest(tag)
         drv.stage(man["stage"], man["dt"])
@@ -61,10 +67,11 @@ def test_stages_match_reference_dumps(name):
             assert np.array_equal(mine, ref["cons"], equal_nan=True), (name, tag, mb["gid"], "cons", fd.relerr(mine, ref["cons"]))
 
 
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("name", CASES)
-def test_floor_and_failure_counts_match_oracle(name):
+def test_floor_and_failure_counts_match_oracle(name, mode):
     """identical floor / ceiling / in-kernel-c2p-failure zone counts (BASELINE.json north_star)"""
-    g, p, mesh, drv, order = _setup(name)
+    g, p, mesh, drv, order = _setup(name, **MODES[mode])
     om = oracle_mesh(g, p)
     for tag in stage_tags(g):
         man = g.manifest(tag)
@@ -137,7 +144,7 @@ def test_tasks_match_oracle(name):
     # --- fused update == divergence + SumData + Average + Update, interior and ghosts
     base, one = mesh.cons["base"], mesh.cons["1"]
     dudt2 = torch.zeros_like(dudt)
-    _lib.check(L.pb_update_fused(pk, cfg, base.data_ptr(), base.data_ptr(), 1.0, dt, one.data_ptr(), dudt2.data_ptr(), None, s))
+    _lib.check(L.pb_update_fused(pk, cfg, base.data_ptr(), base.data_ptr(), 1.0, dt, one.data_ptr(), dudt2.data_ptr(), None, 1, s))
     torch.cuda.synchronize()
     for n, b in blocks:
         c = C.byref(b.cfg)
@@ -145,6 +152,12 @@ def test_tasks_match_oracle(name):
         OL.orc_rk_update(c, b.dudt, b.gsrc.ctypes.data, u0, u0.copy(), 1.0, dt, b.cons["1"])
         assert np.array_equal(_np(one[n]), b.cons["1"])
         assert np.array_equal(_np(dudt2[n])[(slice(None),) + inter], b.dudt[(slice(None),) + inter])
+    # --- the same update from a materialised source container
+    one2, dudt3 = torch.zeros_like(one), torch.zeros_like(dudt)
+    _lib.check(L.pb_update_from_sources(pk, cfg, base.data_ptr(), base.data_ptr(), 1.0, dt, one2.data_ptr(), gsrc.data_ptr(),
+                                        dudt3.data_ptr(), 1, s))
+    torch.cuda.synchronize()
+    assert torch.equal(one2, one) and torch.equal(dudt3, dudt2)
     # --- separate WeightedSumData entry point
     z = torch.empty_like(base)
     _lib.check(L.pb_weighted_sum(base.data_ptr(), one.data_ptr(), 0.5, 0.5, z.data_ptr(), base.numel(), s))

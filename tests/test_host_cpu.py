@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     from phoebus_b200 import _lib
     assert C.sizeof(_lib.PbBlock) == 192
-    assert C.sizeof(_lib.PbPack) == 12 * 8
+    assert C.sizeof(_lib.PbPack) == 16 * 8
 
 
 @pytest.mark.parametrize("name", CASES)
