@@ -67,3 +67,4 @@ build_tree $FMKS FMKS ON
 link_harness $MINK mink
 link_harness $FMKS fmks
 ls -la "$OUT"
+python3 "$HERE/make_decks.py"

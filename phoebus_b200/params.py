@@ -109,7 +109,7 @@ class FluidParams:
             if self.floor_type not in FLOOR:
                 raise ValueError("invalid floor_type")
             self.rho0 = g.real("fixup", "rho0_floor", 0.0)
-            if self.floor_type == "ExpX1RhoU":
+            if self.floor_type in ("ExpX1RhoU", "X1RhoSie", "RRhoSie"):  # ref: fixup.cpp:148-165
                 self.sie0 = g.real("fixup", "u0_floor", 0.0)
                 self.rexp = g.real("fixup", "rho_exp_floor", -2.0)
                 self.sexp = g.real("fixup", "u_exp_floor", -3.0)

@@ -1,0 +1,158 @@
+"""The C++ host layer (phoebus_b200/host): Parthenon-shaped task functions above the C ABI.
+
+CPU part: the library exports the reference's task names, and its deck reader / package Initialize
+functions / Mesh metadata agree bit for bit with the Python mirror (phoebus_b200.params, .mesh).
+GPU part: PhoebusDriver::RungeKuttaStage — fused (pb_rk_stage) and task-by-task in the reference's
+order, per-block tasks on MeshBlockData like the reference's driver — reproduces the reference's
+per-stage dumps bit for bit.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import from_dump as fd
+from tests.helpers import CASES, ROOT, getter, load_case, load_product_state, product_mesh, stage_tags
+
+HOST = os.path.join(ROOT, "phoebus_b200", "host")
+EXE = os.path.join(HOST, "phoebus_host_stage")
+LIBHOST = os.path.join(ROOT, "phoebus_b200", "libphoebus_host.so")
+STATE_FIELDS = ("prim", "temp", "c2p_mu", "fail", "csig", "fsig")
+
+# the reference's task functions a Phoebus build would link against (demangled prefixes)
+TASKS = [
+    "fluid::Initialize(parthenon::ParameterInput*)",
+    "fluid::CalculateFluxes(parthenon::MeshBlockData<double>*)",
+    "fluid::FluxCT(parthenon::MeshBlockData<double>*)",
+    "fluid::CalculateFluidSourceTerms(parthenon::MeshData<double>*, parthenon::MeshData<double>*)",
+    "fluid::PrimitiveToConserved(parthenon::MeshBlockData<double>*)",
+    "fluid::PrimitiveToConservedRegion(parthenon::MeshBlockData<double>*, parthenon::IndexRange const&, parthenon::IndexRange const&, parthenon::IndexRange const&)",
+    "parthenon::TaskStatus fluid::ConservedToPrimitive<parthenon::MeshBlockData<double> >(parthenon::MeshBlockData<double>*)",
+    "parthenon::TaskStatus fluid::ConservedToPrimitive<parthenon::MeshData<double> >(parthenon::MeshData<double>*)",
+    "parthenon::TaskStatus fluid::ConservedToPrimitiveRegion<parthenon::MeshBlockData<double> >(",
+    "parthenon::TaskStatus fluid::ConservedToPrimitiveRobust<parthenon::MeshData<double> >(",
+    "fluid::EstimateTimestepBlock(parthenon::MeshBlockData<double>*)",
+    "fixup::Initialize(parthenon::ParameterInput*)",
+    "fixup::FixFluxes(parthenon::MeshBlockData<double>*)",
+    "parthenon::TaskStatus fixup::ApplyFloors<parthenon::MeshData<double> >(parthenon::MeshData<double>*)",
+    "parthenon::TaskStatus fixup::ApplyFloors<parthenon::MeshBlockData<double> >(parthenon::MeshBlockData<double>*)",
+    "parthenon::TaskStatus fixup::ConservedToPrimitiveFixup<parthenon::MeshData<double> >(parthenon::MeshData<double>*)",
+    "parthenon::TaskStatus fixup::ConservedToPrimitiveFixup<parthenon::MeshBlockData<double> >(parthenon::MeshBlockData<double>*)",
+    "Boundaries::ConvertBoundaryConditions(std::shared_ptr<parthenon::MeshBlockData<double> >&)",
+    "parthenon::TaskStatus parthenon::Update::FluxDivergence<parthenon::MeshData<double> >(parthenon::MeshData<double>*, parthenon::MeshData<double>*)",
+    "parthenon::TaskStatus parthenon::Update::SumData<",
+    "parthenon::TaskStatus parthenon::Update::AverageIndependentData<parthenon::MeshData<double> >(",
+    "parthenon::TaskStatus parthenon::Update::UpdateIndependentData<parthenon::MeshData<double> >(",
+    "parthenon::TaskStatus parthenon::Update::FillDerived<parthenon::MeshBlockData<double> >(",
+    "parthenon::SendBoundBufs(std::shared_ptr<parthenon::MeshData<double> >&)",
+    "phoebus::PhoebusDriver::RungeKuttaStage(int)",
+]
+
+
+def _deck_text(pin):
+    out = []
+    for blk, kv in pin.blocks.items():
+        out.append("<%s>" % blk)
+        out += ["%s = %s" % (k, v) for k, v in kv.items()]
+        out.append("")
+    return "\n".join(out)
+
+
+def _case_deck(name, tmp_path):
+    from tests.helpers import product_params
+    from phoebus_b200.params import ParameterInput
+    g, _ = load_case(name)
+    fp = product_params(g)
+    # product_params mutates a ParameterInput built from the fixture; rebuild the same blocks here
+    pin = ParameterInput.from_blocks(g.meta["deck_blocks"])
+    man = g.manifest("init")
+    mesh = pin.blocks.setdefault("parthenon/mesh", {})
+    for k, v in man["mesh"].items():
+        mesh[k] = repr(float(v))
+    pin.blocks.setdefault("geometry", {})["kind"] = "fmks" if g.meta["geometry"] == 1 else "minkowski"
+    path = os.path.join(str(tmp_path), name + ".pin")
+    with open(path, "w") as f:
+        f.write(_deck_text(pin))
+    return g, fp, path
+
+
+def test_host_library_is_built_and_exports_the_reference_task_names():
+    assert os.path.exists(LIBHOST) and os.path.exists(EXE), "build with `make -C phoebus_b200/host`"
+    syms = subprocess.run(["nm", "-DC", "--defined-only", LIBHOST], capture_output=True, text=True, check=True).stdout
+    missing = [t for t in TASKS if t not in syms]
+    assert not missing, missing
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_host_cfg_and_mesh_metadata_match_python_mirror(name, tmp_path):
+    from phoebus_b200._lib import PbBlock
+    g, fp, deck = _case_deck(name, tmp_path)
+    mesh, _ = product_mesh(g, alloc_fields=False)
+    tab = os.path.join(str(tmp_path), "tables.bin")
+    r = subprocess.run([EXE, "describe", deck, tab], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = {ln.split()[0]: ln.split()[1:] for ln in r.stdout.splitlines() if ln.strip()}
+    cfg = mesh.cfg
+    for key, _ctype in cfg._fields_:
+        v = getattr(cfg, key)
+        if key == "nx":
+            assert [int(x) for x in got["nx"]] == list(v)
+        elif isinstance(v, float):
+            assert float(got[key][0]) == v, key
+        else:
+            assert int(got[key][0]) == v, key
+    assert int(got["nblocks"][0]) == mesh.nblocks
+    raw = open(tab, "rb").read()
+    nb = C.sizeof(PbBlock) * mesh.nblocks
+    assert raw[:nb] == bytes(mesh.blocks_host), "block table (coordinates, bc codes, slots, neighbours)"
+    rest = np.frombuffer(raw[nb:], dtype=np.float64)
+    ng = mesh.geom_host.size
+    assert np.array_equal(rest[:ng], mesh.geom_host.ravel(), equal_nan=True), "geometry tables"
+    assert np.array_equal(rest[ng:], mesh.floor_host.ravel(), equal_nan=True), "floor tables"
+
+
+def test_host_rejects_what_the_reference_rejects(tmp_path):
+    deck = os.path.join(str(tmp_path), "bad.pin")
+    open(deck, "w").write("<parthenon/mesh>\nnx1 = 64\nnghost = 2\n<fluid>\nrecon = weno5\n")
+    r = subprocess.run([EXE, "describe", deck, os.devnull], capture_output=True, text=True)
+    assert r.returncode != 0 and "requires 4+ ghost cells" in r.stderr
+    r = subprocess.run([EXE, "describe", deck, os.devnull, "fluid/recon=ppm", "parthenon/mesh/nghost=4"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Reconstruction method invalid" in r.stderr
+    r = subprocess.run([EXE, "describe", deck, os.devnull, "fluid/recon=linear", "parthenon/meshblock/nx1=48"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not evenly divisible" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fused", "tasks"])
+@pytest.mark.parametrize("name", CASES)
+def test_host_driver_matches_reference_dumps(name, mode, tmp_path):
+    import torch
+    assert torch.cuda.is_available()
+    g, fp, deck = _case_deck(name, tmp_path)
+    mesh, _ = product_mesh(g, device=torch.device("cuda:0"))
+    order = load_product_state(mesh, g, "init")
+    fields = [getattr(mesh, k) for k in STATE_FIELDS] + [mesh.cons["base"], mesh.cons["1"]]
+    sin, sout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
+    with open(sin, "wb") as f:
+        for t in fields:
+            f.write(t.cpu().numpy().tobytes())
+    tags = stage_tags(g)
+    for ntag in range(1, len(tags) + 1):
+        stages = ",".join("%d:%r" % (g.manifest(t)["stage"], float(g.manifest(t)["dt"])) for t in tags[:ntag])
+        r = subprocess.run([EXE, "run", deck, sin, sout, mode, stages], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr + r.stdout
+        raw = np.fromfile(sout, dtype=np.float64)
+        off, out = 0, {}
+        for k, t in zip(STATE_FIELDS + ("base", "1"), fields):
+            out[k] = raw[off:off + t.numel()].reshape(tuple(t.shape))
+            off += t.numel()
+        tag = tags[ntag - 1]
+        man = g.manifest(tag)
+        for mb in man["blocks"]:
+            n = order[mb["gid"]]
+            ref = fd.ref_state(getter(g, tag), mb["gid"], mesh.shape, man["sc1"])
+            for k in ("prim", "temp", "c2p_mu", "fail", "csig"):
+                assert np.array_equal(out[k][n].reshape(ref[k].shape), ref[k], equal_nan=True), (name, mode, tag, k)
+            assert np.array_equal(out[man["sc1"]][n], ref["cons"], equal_nan=True), (name, mode, tag, "cons")
