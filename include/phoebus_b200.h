@@ -226,7 +226,20 @@ int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1,
 #define PB_TASK_FIXUP_FLOORS 8
 #define PB_NTASK 9
 int pb_profile_enable(int on);
+/* Device self-test of the library's deferred-branch FP64 divide / reciprocal / square root against
+ * IEEE a/b, 1.0/x, sqrt(x) on n pseudo-random operand pairs with exponents in +-exponent_span.
+ * counts_dev (device, 5 x uint64, caller zeroes): mismatches of div, divz, rcp, root; [4] = cases
+ * routed to the exact path. The hot path relies on [0..3] being zero (bit parity with the reference). */
+int pb_selftest_arith(long long n, unsigned long long seed, int exponent_span, unsigned long long *counts_dev,
+                      void *stream);
 int pb_profile_read(double ms[PB_NTASK], int calls[PB_NTASK]);
+
+/* Same idea one level up: riemann.hpp's prim_to_flux (face state -> U, F, v+-) evaluated with the
+ * deferred-branch arithmetic and with the compiler's, on n synthetic MHD face states (flat != 0:
+ * Minkowski metric; else a random metric). counts_dev[0] = states whose outputs differ in any bit,
+ * [1] = states routed to the exact path; first_dev (16 doubles): the first differing case. */
+int pb_selftest_riemann(long long n, unsigned long long seed, const pb_cfg_t *cfg, int flat,
+                        unsigned long long *counts_dev, double *first_dev, void *stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,19 @@
 
 namespace pb {
 
+// debugging switches: -DPB_FLUX_RECON_EXACT / -DPB_FLUX_RIEMANN_EXACT build the phase with the
+// compiler's own divide / sqrt expansion (same bits, slower)
+#ifdef PB_FLUX_RECON_EXACT
+typedef ArithExact ArithRecon;
+#else
+typedef ArithFast ArithRecon;
+#endif
+#ifdef PB_FLUX_RIEMANN_EXACT
+typedef ArithExact ArithRiemann;
+#else
+typedef ArithFast ArithRiemann;
+#endif
+
 struct FluxTile {
   int NS;      // cells along the stencil axis handled per pencil (n + 2)
   int TT;      // pencils per CTA
@@ -63,12 +76,24 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
   Real qR[NP];
   if (valid) {
     const Real *v = pack.prim + (size_t)b * NP * L.ncell + o;
+    ArithRecon af;
 #pragma unroll
     for (int n = 0; n < NP; ++n) {
       const Real *p = v + (size_t)n * L.ncell;
       Real ql;
-      recon5<RECON>(__ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), ql, qR[n]);
+      recon5<RECON>(af, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), ql, qR[n]);
       s_ql[n * plane + slot_w] = ql;
+    }
+    if (af.failed()) { // an operand outside the fast divide's exponent range: redo with the compiler's a/b
+      ArithExact ax;
+#pragma unroll 1
+      for (int n = 0; n < NP; ++n) {
+        const Real *p = v + (size_t)n * L.ncell;
+        Real ql, qr;
+        recon5<RECON>(ax, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), ql, qr);
+        s_ql[n * plane + slot_w] = ql;
+        qR[n] = qr;
+      }
     }
   }
   __syncthreads();
@@ -97,8 +122,16 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
   fc.x3 = (DIR == 3) ? Xf(blk, 2, k) : Xc(blk, 2, k);
 
   Real Ul[NCn], Fl[NCn], Ur[NCn], Fr[NCn], vml, vpl, vmr, vpr;
-  prim_to_flux<DIR, MHD>(cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
-  prim_to_flux<DIR, MHD>(cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+  {
+    ArithRiemann af;
+    prim_to_flux<DIR, MHD>(af, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
+    prim_to_flux<DIR, MHD>(af, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+    if (af.failed()) {
+      ArithExact ax;
+      prim_to_flux<DIR, MHD>(ax, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
+      prim_to_flux<DIR, MHD>(ax, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+    }
+  }
   Real *fl = pack.flux + ((size_t)b * L.ndim + (DIR - 1)) * NCn * L.ncell + o;
   Real speed;
   if (cfg.riemann == 0) { // llf, ref: riemann.hpp:256-276

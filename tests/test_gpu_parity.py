@@ -235,3 +235,39 @@ def test_recon_schemes_through_flux_kernel():
                 OL.orc_calculate_fluxes(C.byref(b.cfg), b.geom, b.prim, b.flux, b.fsig)
                 assert np.array_equal(_np(mesh.flux[n]), b.flux), (recon, riemann, fd.relerr(_np(mesh.flux[n]), b.flux))
                 assert np.array_equal(_np(mesh.fsig[n]), b.fsig)
+
+
+@pytest.mark.parametrize("span", [8, 300, 1000])
+def test_fast_divide_sqrt_are_ieee_exact(span):
+    """ArithFast (deferred range check) must return the bits of IEEE a/b, 1/x, sqrt(x) wherever it
+    accepts its operands; everything else is routed to the compiler's own sequences."""
+    import torch
+    from phoebus_b200 import _lib
+    L = _lib.lib()
+    counts = torch.zeros(5, dtype=torch.int64, device=_dev())
+    n = 1 << 24
+    _lib.check(L.pb_selftest_arith(n, 1234 + span, span, counts.data_ptr(), None), "pb_selftest_arith")
+    torch.cuda.synchronize()
+    c = counts.cpu().tolist()
+    assert c[:4] == [0, 0, 0, 0], c
+    assert c[4] < 5 * n, c
+    if span <= 300:  # operands well inside the exponent range: only the +-0 numerators of div() are rejected
+        assert c[4] < n, c
+
+
+@pytest.mark.parametrize("flat", [1, 0])
+@pytest.mark.parametrize("name", ["blast3d", "torus2d"])
+def test_fast_arith_riemann_states_bit_identical(name, flat):
+    import torch
+    from phoebus_b200 import _lib
+    g, p = load_case(name)
+    mesh, fp = product_mesh(g, device=_dev(), alloc_fields=False)
+    L = _lib.lib()
+    counts = torch.zeros(2, dtype=torch.int64, device=_dev())
+    first = torch.zeros(16, dtype=torch.float64, device=_dev())
+    n = 1 << 22
+    _lib.check(L.pb_selftest_riemann(n, 99, C.byref(mesh.cfg), flat, counts.data_ptr(), first.data_ptr(), None), "pb_selftest_riemann")
+    torch.cuda.synchronize()
+    c = counts.cpu().tolist()
+    assert c[0] == 0, (c, first.cpu().tolist())
+    assert c[1] < n // 2, c
