@@ -108,6 +108,10 @@ typedef struct pb_pack {
   int n_bc_blocks;
   double *gsrc;             /* [b][4][cells] the "geometric source terms" container (ref: phoebus_driver.cpp:289-299);
                              * when present the sequencer runs the sources as their own launch */
+  double *recon_lr;         /* [2][b][nprim][cells] left / right face states of ONE direction at a time (the
+                             * reference's ql / qr fields, ref: src/fluid/fluid.cpp:288-299). When present,
+                             * pb_calculate_fluxes runs reconstruction and Riemann solve as two launches per
+                             * direction (higher occupancy for the reconstruction); NULL: one fused launch */
 } pb_pack_t;
 
 const char *pb_version(void);

@@ -44,7 +44,8 @@ class PbPack(C.Structure):
     _fields_ = [("nblocks", C.c_int), ("blocks", C.c_void_p), ("geom", C.c_void_p), ("floor_tab", C.c_void_p),
                 ("prim", C.c_void_p), ("temp", C.c_void_p), ("c2p_mu", C.c_void_p), ("fail", C.c_void_p),
                 ("csig", C.c_void_p), ("fsig", C.c_void_p), ("flux", C.c_void_p), ("emf", C.c_void_p),
-                ("zflags", C.c_void_p), ("bc_blocks", C.c_void_p), ("n_bc_blocks", C.c_int), ("gsrc", C.c_void_p)]
+                ("zflags", C.c_void_p), ("bc_blocks", C.c_void_p), ("n_bc_blocks", C.c_int), ("gsrc", C.c_void_p),
+                ("recon_lr", C.c_void_p)]
 
 
 # every symbol include/phoebus_b200.h declares: name -> (restype, argtypes)

@@ -48,6 +48,13 @@ int flux_threads_target() {
   static int v = env_int("PB_FLUX_THREADS", 272);
   return v;
 }
+bool flux_split_enabled() { // PB_FLUX_MODE=fused forces the one-launch kernel even when the pack has ql/qr scratch
+  static int v = [] {
+    const char *e = getenv("PB_FLUX_MODE");
+    return (e && e[0] == 'f') ? 0 : 1;
+  }();
+  return v != 0;
+}
 int zone_threads() {
   static int v = env_int("PB_ZONE_THREADS", 128);
   return v > 128 ? 128 : v; // zone kernels are compiled with __launch_bounds__(128, n)

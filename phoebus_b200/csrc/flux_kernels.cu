@@ -32,15 +32,32 @@ struct FluxTile {
   int tiles;   // CTAs per block
 };
 
-// 2 CTAs of <= 288 threads per SM: 96 registers (measured optimum on B200, profiles/r1_tuning.md)
+// ---- asynchronous global -> shared staging (LDGSTS): the copies bypass registers, so a CTA has its
+// whole stencil tile and its face geometry in flight at once instead of 50 dependent loads per thread
+PB_DEV void cp_async8(Real *smem_dst, const Real *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+PB_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> PB_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int FLUX_NGEO = 19; // alpha, detgam, beta[3], gcov[10], gamma^{dd}, floor A, floor B, (pad)
+
+// Shared memory of one CTA (doubles):
+//   s_in  [NP][(NS+4)*TT]  primitives of the tile's stencil pencils, 2 extra cells at either end
+//   s_ql  [NP][(NS+1)*TT]  left-face states handed to the neighbouring thread
+//   s_geo [FLUX_NGEO][NS*TT] this thread's face geometry + floor-table entries
+// 2 CTAs of <= 288 threads per SM: 96 registers (measured optimum on B200, profiles/r01_sweep2*)
 template <int DIR, int RECON, bool MHD>
 __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const FluxTile ft) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
-  extern __shared__ Real s_ql[]; // [NP][(NS+1)*TT]
+  extern __shared__ Real smem[];
   const Lay L(cfg);
   const int b = blockIdx.x / ft.tiles, tile = blockIdx.x % ft.tiles;
   const int NS = ft.NS, TT = ft.TT;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = NS * TT;
+  const int plane_in = (NS + 4) * TT, plane = (NS + 1) * TT;
+  Real *s_in = smem, *s_ql = smem + NP * plane_in, *s_geo = s_ql + NP * plane;
   int sI, tI;
   if (DIR == 1) {
     sI = tid % NS;
@@ -69,54 +86,89 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
     k = L.ks - 1 + sI;
     st = L.ni * L.nj;
   }
-  const int plane = (NS + 1) * TT;
+  // entry e of pencil tI in s_in <-> cell (sI = e - 2); my own cell is entry sI + 2
+  const int in0 = (DIR == 1) ? tI * (NS + 4) + sI : sI * TT + tI;
+  const int in_st = (DIR == 1) ? 1 : TT;
   const int slot_w = (DIR == 1) ? tI * (NS + 1) + sI + 1 : (sI + 1) * TT + tI; // my ql goes to face s+1
   const int slot_r = (DIR == 1) ? tI * (NS + 1) + sI : sI * TT + tI;           // face s reads cell s-1's ql
   const int o = L.idx(k, j, i);
-  Real qR[NP];
+  const pb_block_t &blk = pack.blocks[b];
   if (valid) {
     const Real *v = pack.prim + (size_t)b * NP * L.ncell + o;
-    ArithRecon af;
 #pragma unroll
     for (int n = 0; n < NP; ++n) {
       const Real *p = v + (size_t)n * L.ncell;
+      Real *d = s_in + n * plane_in + in0;
+      cp_async8(d + 2 * in_st, p);
+      if (sI < 2) cp_async8(d, p - 2 * st);
+      if (sI >= NS - 2) cp_async8(d + 4 * in_st, p + 2 * st);
+    }
+  }
+  cp_async_commit();
+  if (valid && sI > 0) {
+    // FaceGeom (ref: riemann.hpp:32-54): only gamma^{dd} of the inverse metric is needed
+    const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+    const int gcell = gt.cell(k, j, i);
+    const Real *gp = gt.t + (size_t)(DIR * PB_NGLOC) * gt.gcell + gcell;
+    Real *d = s_geo + tid;
+    cp_async8(d, gp + (size_t)G_ALPHA * gt.gcell);
+    cp_async8(d + nthr, gp + (size_t)G_DETGAM * gt.gcell);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) cp_async8(d + (2 + m) * nthr, gp + (size_t)(G_BCON + m) * gt.gcell);
+#pragma unroll
+    for (int m = 0; m < 10; ++m) cp_async8(d + (5 + m) * nthr, gp + (size_t)(G_GCOV + m) * gt.gcell);
+    cp_async8(d + 15 * nthr, gp + (size_t)(G_GAMCON + flat4(DIR - 1, DIR - 1)) * gt.gcell);
+    const Real *fp = pack.floor_tab + ((size_t)blk.floor_slot * 4 + (DIR == 1 ? 2 : 0)) * L.ni + i;
+    cp_async8(d + 16 * nthr, fp);
+    cp_async8(d + 17 * nthr, fp + L.ni);
+  }
+  cp_async_commit();
+  cp_async_wait<1>(); // the stencil tile has landed (the geometry may still be in flight)
+  __syncthreads();
+
+  Real qR[NP];
+  if (valid) {
+    const Real *c = s_in + in0;
+    ArithRecon af;
+#pragma unroll
+    for (int n = 0; n < NP; ++n) {
+      const Real *q = c + n * plane_in;
       Real ql;
-      recon5<RECON>(af, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), ql, qR[n]);
+      recon5<RECON>(af, q[0], q[in_st], q[2 * in_st], q[3 * in_st], q[4 * in_st], ql, qR[n]);
       s_ql[n * plane + slot_w] = ql;
     }
     if (af.failed()) { // an operand outside the fast divide's exponent range: redo with the compiler's a/b
       ArithExact ax;
 #pragma unroll 1
       for (int n = 0; n < NP; ++n) {
-        const Real *p = v + (size_t)n * L.ncell;
+        const Real *q = c + n * plane_in;
         Real ql, qr;
-        recon5<RECON>(ax, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), ql, qr);
+        recon5<RECON>(ax, q[0], q[in_st], q[2 * in_st], q[3 * in_st], q[4 * in_st], ql, qr);
         s_ql[n * plane + slot_w] = ql;
         qR[n] = qr;
       }
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
   if (!valid || sI == 0) return;
   Real qL[NP];
 #pragma unroll
   for (int n = 0; n < NP; ++n) qL[n] = s_ql[n * plane + slot_r];
 
-  const pb_block_t &blk = pack.blocks[b];
-  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
   PointGeom g;
-  const int gcell = gt.cell(k, j, i);
-  // FaceGeom (ref: riemann.hpp:32-54): only gamma^{dd} of the inverse metric is needed
-  g.alpha = gt.at(DIR, G_ALPHA, gcell);
-  g.detgam = gt.at(DIR, G_DETGAM, gcell);
+  const Real *sg = s_geo + tid;
+  g.alpha = sg[0];
+  g.detgam = sg[nthr];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) g.beta[d] = gt.at(DIR, G_BCON + d, gcell);
+  for (int d = 0; d < 3; ++d) g.beta[d] = sg[(2 + d) * nthr];
 #pragma unroll
-  for (int m = 0; m < 10; ++m) g.gcov[m] = gt.at(DIR, G_GCOV + m, gcell);
-  const Real gdd = gt.at(DIR, G_GAMCON + flat4(DIR - 1, DIR - 1), gcell);
+  for (int m = 0; m < 10; ++m) g.gcov[m] = sg[(5 + m) * nthr];
+  const Real gdd = sg[15 * nthr];
   const Real gdet = g.alpha * g.detgam; // DetG = alpha * sqrt(gamma), cached_system.hpp:371-374
   FloorCtx fc;
-  load_floor(pack.floor_tab, blk.floor_slot, L.ni, DIR == 1 ? 1 : 0, i, fc.A, fc.B);
+  fc.A = sg[16 * nthr];
+  fc.B = sg[17 * nthr];
   fc.x1 = (DIR == 1) ? Xf(blk, 0, i) : Xc(blk, 0, i);
   fc.x2 = (DIR == 2) ? Xf(blk, 1, j) : Xc(blk, 1, j);
   fc.x3 = (DIR == 3) ? Xf(blk, 2, k) : Xc(blk, 2, k);
@@ -181,7 +233,7 @@ static int launch_dir(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s
   if (ft.NS * ft.TT > 288) return set_error(PB_EINVAL, "block too large for the flux tile");
   ft.tiles = (ft.nT + ft.TT - 1) / ft.TT;
   const int threads = ft.NS * ft.TT;
-  const size_t smem = (size_t)NC<MHD>::nprim * (ft.NS + 1) * ft.TT * sizeof(Real);
+  const size_t smem = ((size_t)NC<MHD>::nprim * ((ft.NS + 1) + (ft.NS + 4)) * ft.TT + (size_t)FLUX_NGEO * threads) * sizeof(Real);
   auto kern = flux_kernel<DIR, RECON, MHD>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -210,6 +262,10 @@ template <bool MHD> static int launch_recon(const pb_pack_t &pack, const pb_cfg_
 
 } // namespace pb
 
+namespace pb {
+int calculate_fluxes_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s); // flux_split_kernels.cu
+}
+
 extern "C" int pb_calculate_fluxes(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream) {
   using namespace pb;
   int rc = check_args(pack, cfg);
@@ -217,5 +273,6 @@ extern "C" int pb_calculate_fluxes(const pb_pack_t *pack, const pb_cfg_t *cfg, v
   if (cfg->ng < 3 && cfg->recon >= 2) return set_error(PB_EINVAL, "weno5/mp5 need nghost >= 3");
   if (cfg->riemann != 0 && cfg->riemann != 1) return set_error(PB_EINVAL, "unknown riemann solver");
   cudaStream_t s = (cudaStream_t)stream;
+  if (pack->recon_lr && flux_split_enabled()) return calculate_fluxes_split(*pack, *cfg, s);
   return cfg->mhd ? launch_recon<true>(*pack, *cfg, s) : launch_recon<false>(*pack, *cfg, s);
 }

@@ -1,0 +1,189 @@
+// fluid::CalculateFluxes as two launches per direction (ref: src/fluid/fluid.cpp:659-773):
+//   recon_kernel   one cell per thread: reconstructs the 7/10 primitives along DIR and writes the
+//                  left/right face states into the pack's ql/qr scratch (the reference's ql / qr
+//                  fields, fluid.cpp:288-299, one direction at a time);
+//   riemann_kernel one face per thread: prim_to_flux on both states + LLF/HLL (riemann.hpp:87-301).
+// Why two launches when flux_kernels.cu fuses them: the path is FP64-latency bound, not HBM bound.
+// Reconstruction is 75 % of the FP64 work and needs < 64 registers, the Riemann solve needs > 110;
+// fused, the whole kernel runs at the Riemann solve's occupancy (17 warps/SM, FP64 pipe 50 % busy).
+// Split, reconstruction runs at 2-3x the occupancy; the ql/qr round trip (40 words per zone and
+// direction) hides under the arithmetic (measured: profiles/r01_flux_split*.md).
+#include "pb_device.cuh"
+#include "pb_host.hpp"
+
+namespace pb {
+
+struct Box { // inclusive cell ranges of one block
+  int i0, i1, j0, j1, k0, k1;
+  __host__ __device__ int ni() const { return i1 - i0 + 1; }
+  __host__ __device__ int nj() const { return j1 - j0 + 1; }
+  __host__ __device__ long long n() const { return (long long)ni() * nj() * (k1 - k0 + 1); }
+};
+PB_DEV bool cell_of_thread(const Box &r, int nblocks, int &b, int &k, int &j, int &i) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nreg = r.n();
+  if (t >= nreg * nblocks) return false;
+  b = (int)(t / nreg);
+  int rem = (int)(t - (long long)b * nreg);
+  const int q = rem / r.ni();
+  i = r.i0 + (rem - q * r.ni());
+  const int q2 = q / r.nj();
+  j = r.j0 + (q - q2 * r.nj());
+  k = r.k0 + q2;
+  return true;
+}
+
+#ifndef PB_RECON_MINB
+#define PB_RECON_MINB 4
+#endif
+#ifndef PB_RIEMANN_MINB
+#define PB_RIEMANN_MINB 2
+#endif
+
+template <int DIR, int RECON, int NP>
+__global__ void __launch_bounds__(256, PB_RECON_MINB) recon_kernel(const Real *__restrict__ prim, Real *__restrict__ ql,
+                                                                   Real *__restrict__ qr, const pb_cfg_t cfg, const Box reg,
+                                                                   const int nblocks) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!cell_of_thread(reg, nblocks, b, k, j, i)) return;
+  const int st = DIR == 1 ? 1 : (DIR == 2 ? L.ni : L.ni * L.nj);
+  const size_t o = (size_t)b * NP * L.ncell + L.idx(k, j, i);
+  const Real *v = prim + o;
+  Real *l = ql + o + st; // my left state belongs to the face of cell s+1
+  Real *r = qr + o;
+  ArithFast af;
+#pragma unroll
+  for (int n = 0; n < NP; ++n) {
+    const Real *p = v + (size_t)n * L.ncell;
+    Real a, c;
+    recon5<RECON>(af, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), a, c);
+    l[(size_t)n * L.ncell] = a;
+    r[(size_t)n * L.ncell] = c;
+  }
+  if (af.failed()) { // operands outside the fast divide's range: redo with the compiler's a/b
+    ArithExact ax;
+#pragma unroll 1
+    for (int n = 0; n < NP; ++n) {
+      const Real *p = v + (size_t)n * L.ncell;
+      Real a, c;
+      recon5<RECON>(ax, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), a, c);
+      l[(size_t)n * L.ncell] = a;
+      r[(size_t)n * L.ncell] = c;
+    }
+  }
+}
+
+template <int DIR, bool MHD>
+__global__ void __launch_bounds__(256, PB_RIEMANN_MINB) riemann_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Box reg,
+                                                                       const Real *__restrict__ ql, const Real *__restrict__ qr) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!cell_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  const pb_block_t &blk = pack.blocks[b];
+  Real qL[NP], qR[NP];
+  {
+    const size_t q0 = (size_t)b * NP * L.ncell + o;
+#pragma unroll
+    for (int n = 0; n < NP; ++n) {
+      qL[n] = __ldg(ql + q0 + (size_t)n * L.ncell);
+      qR[n] = __ldg(qr + q0 + (size_t)n * L.ncell);
+    }
+  }
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  const int gcell = gt.cell(k, j, i);
+  // FaceGeom (ref: riemann.hpp:32-54): only gamma^{dd} of the inverse metric is needed
+  g.alpha = gt.at(DIR, G_ALPHA, gcell);
+  g.detgam = gt.at(DIR, G_DETGAM, gcell);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) g.beta[d] = gt.at(DIR, G_BCON + d, gcell);
+#pragma unroll
+  for (int m = 0; m < 10; ++m) g.gcov[m] = gt.at(DIR, G_GCOV + m, gcell);
+  const Real gdd = gt.at(DIR, G_GAMCON + flat4(DIR - 1, DIR - 1), gcell);
+  const Real gdet = g.alpha * g.detgam; // DetG = alpha * sqrt(gamma), cached_system.hpp:371-374
+  FloorCtx fc;
+  load_floor(pack.floor_tab, blk.floor_slot, L.ni, DIR == 1 ? 1 : 0, i, fc.A, fc.B);
+  fc.x1 = (DIR == 1) ? Xf(blk, 0, i) : Xc(blk, 0, i);
+  fc.x2 = (DIR == 2) ? Xf(blk, 1, j) : Xc(blk, 1, j);
+  fc.x3 = (DIR == 3) ? Xf(blk, 2, k) : Xc(blk, 2, k);
+
+  Real Ul[NCn], Fl[NCn], Ur[NCn], Fr[NCn], vml, vpl, vmr, vpr;
+  {
+    ArithFast af;
+    prim_to_flux<DIR, MHD>(af, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
+    prim_to_flux<DIR, MHD>(af, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+    if (af.failed()) {
+      ArithExact ax;
+      prim_to_flux<DIR, MHD>(ax, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
+      prim_to_flux<DIR, MHD>(ax, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+    }
+  }
+  Real *fl = pack.flux + ((size_t)b * L.ndim + (DIR - 1)) * NCn * L.ncell + o;
+  Real speed;
+  if (cfg.riemann == 0) { // llf, ref: riemann.hpp:256-276
+    const Real cmax = dmax(dmax(-vml, vpl), dmax(-vmr, vpr));
+#pragma unroll
+    for (int m = 0; m < NCn; m++)
+      fl[(size_t)m * L.ncell] = 0.5 * ((Fl[m] + Fr[m]) * gdet - cmax * ((Ur[m] - Ul[m]) * g.detgam));
+    speed = cmax;
+  } else { // hll, ref: riemann.hpp:278-301
+    const Real cl = dmin(dmin(vml, vmr), 0.0);
+    const Real cr = dmax(dmax(vpl, vpr), 0.0);
+    const Real crcl = cr * cl;
+    const Real inv_cr_cl = ratio(1.0, cr - cl);
+#pragma unroll
+    for (int m = 0; m < NCn; m++)
+      fl[(size_t)m * L.ncell] = ((cr * Fl[m] - cl * Fr[m]) * gdet + crcl * (Ur[m] - Ul[m]) * g.detgam) * inv_cr_cl;
+    speed = dmax(-cl, cr);
+  }
+  pack.fsig[((size_t)b * L.ndim + (DIR - 1)) * L.ncell + o] = speed;
+}
+
+template <int DIR, int RECON, bool MHD>
+static int launch_dir_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
+  constexpr int NP = NC<MHD>::nprim;
+  const Lay L(cfg);
+  // cells reconstructed: one layer beyond the interior along DIR; transverse extent as the
+  // reference's flux loops (faces in the first ghost layer feed FluxCT), ref: fluid.cpp:700-720
+  Box rc;
+  if (DIR == 1) rc = Box{L.is - 1, L.ie + 1, L.js - L.dj, L.je + L.dj, L.ks - L.dk, L.ke + L.dk};
+  else if (DIR == 2) rc = Box{L.is - 1, L.ie + 1, L.js - 1, L.je + 1, L.ks - L.dk, L.ke + L.dk};
+  else rc = Box{L.is - 1, L.ie + 1, L.js - 1, L.je + 1, L.ks - 1, L.ke + 1};
+  Box rf = rc; // faces: drop the first cell along DIR
+  if (DIR == 1) rf.i0 += 1;
+  else if (DIR == 2) rf.j0 += 1;
+  else rf.k0 += 1;
+  Real *ql = pack.recon_lr, *qr = pack.recon_lr + (size_t)pack.nblocks * NP * L.ncell;
+  const int T = 256;
+  const long long n1 = rc.n() * pack.nblocks, n2 = rf.n() * pack.nblocks;
+  recon_kernel<DIR, RECON, NP><<<(unsigned)((n1 + T - 1) / T), T, 0, s>>>(pack.prim, ql, qr, cfg, rc, pack.nblocks);
+  int rcode = check_launch("recon_kernel");
+  if (rcode) return rcode;
+  riemann_kernel<DIR, MHD><<<(unsigned)((n2 + T - 1) / T), T, 0, s>>>(pack, cfg, rf, ql, qr);
+  return check_launch("riemann_kernel");
+}
+
+template <int RECON, bool MHD> static int launch_all_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
+  int rc = launch_dir_split<1, RECON, MHD>(pack, cfg, s);
+  if (rc == 0 && cfg.ndim >= 2) rc = launch_dir_split<2, RECON, MHD>(pack, cfg, s);
+  if (rc == 0 && cfg.ndim >= 3) rc = launch_dir_split<3, RECON, MHD>(pack, cfg, s);
+  return rc;
+}
+template <bool MHD> static int launch_recon_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
+  switch (cfg.recon) {
+  case 0: return launch_all_split<0, MHD>(pack, cfg, s);
+  case 1: return launch_all_split<1, MHD>(pack, cfg, s);
+  case 2: return launch_all_split<2, MHD>(pack, cfg, s);
+  case 3: return launch_all_split<3, MHD>(pack, cfg, s);
+  }
+  return set_error(PB_EINVAL, "unknown reconstruction");
+}
+
+int calculate_fluxes_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
+  return cfg.mhd ? launch_recon_split<true>(pack, cfg, s) : launch_recon_split<false>(pack, cfg, s);
+}
+
+} // namespace pb

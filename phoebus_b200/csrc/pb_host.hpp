@@ -17,6 +17,7 @@ int check_args(const pb_pack_t *pack, const pb_cfg_t *cfg);
 // tunables (environment overrides, read once): PB_FLUX_THREADS, PB_ZONE_THREADS
 int flux_threads_target();
 int zone_threads();
+bool flux_split_enabled(); // PB_FLUX_MODE=fused|split (default split when the pack carries ql/qr scratch)
 
 } // namespace pb
 #endif

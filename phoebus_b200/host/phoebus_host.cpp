@@ -547,6 +547,7 @@ void Mesh::Allocate() {
   pack_.bc_blocks = bcb_dev;
   pack_.n_bc_blocks = (int)bcb.size();
   pack_.gsrc = field_["gsrc"];
+  pack_.recon_lr = (double *)dev((size_t)2 * nblocks * nprim * cells * 8); // ql / qr of one direction
   AddContainer("base");
   AddContainer("1");
   AddContainer("dUdt");
@@ -606,6 +607,7 @@ std::shared_ptr<MeshBlockData<Real>> Mesh::GetBlockData(int b, const std::string
   p.emf += o * 3;
   p.zflags += o;
   p.gsrc += o * 4;
+  p.recon_lr = nullptr; // per-block calls use the fused flux kernel
   p.bc_blocks = nullptr; // "every block of this pack"
   p.n_bc_blocks = 0;
   rc->pack = p;

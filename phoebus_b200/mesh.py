@@ -54,13 +54,13 @@ def rank_grid(world, nblk, ndim):
 
 class MeshPack:
     def __init__(self, params, device=None, rank=0, world=1, mesh_xmin=None, mesh_xmax=None, geom_par=None,
-                 alloc_fields=True, use_zflags=True, use_gsrc=True):
+                 alloc_fields=True, use_zflags=True, use_gsrc=True, use_recon_lr=True):
         import torch
         self.torch = torch
         self.p = params
         self.rank, self.world = rank, world
         self.device = device
-        self.use_zflags, self.use_gsrc = use_zflags, use_gsrc
+        self.use_zflags, self.use_gsrc, self.use_recon_lr = use_zflags, use_gsrc, use_recon_lr
         p = params
         self.ndim, self.ng = p.ndim, p.ng
         self.nx = tuple(p.block_nx)
@@ -256,6 +256,8 @@ class MeshPack:
         # accelerators of the sequencer (include/phoebus_b200.h): zone flags, sources container
         self.zflags = t.zeros((nb,) + self.shape, dtype=t.uint8, device=dev) if self.use_zflags else None
         self.gsrc = z(4) if self.use_gsrc else None
+        # ql / qr scratch of the two-launch flux path (one direction at a time)
+        self.recon_lr = t.empty((2, nb, self.nprim) + self.shape, dtype=t.float64, device=dev) if self.use_recon_lr else None
         self.flags_valid = False
         self.counters = t.zeros(3, dtype=t.int64, device=dev)
         self.dt_dev = t.zeros(1, dtype=t.float64, device=dev)
@@ -279,6 +281,7 @@ class MeshPack:
             setattr(pk, name, getattr(self, name).data_ptr())
         pk.zflags = self.zflags.data_ptr() if self.zflags is not None else None
         pk.gsrc = self.gsrc.data_ptr() if self.gsrc is not None else None
+        pk.recon_lr = self.recon_lr.data_ptr() if self.recon_lr is not None else None
         pk.bc_blocks = self.bc_blocks.data_ptr()
         pk.n_bc_blocks = self.n_bc_blocks
         self.pack = pk
@@ -290,7 +293,7 @@ class MeshPack:
 
     def bytes_allocated(self):
         n = 0
-        for name in ("prim", "temp", "c2p_mu", "fail", "csig", "fsig", "flux", "emf", "geom", "floor_tab", "gsrc"):
+        for name in ("prim", "temp", "c2p_mu", "fail", "csig", "fsig", "flux", "emf", "geom", "floor_tab", "gsrc", "recon_lr"):
             if getattr(self, name) is not None:
                 n += getattr(self, name).numel() * 8
         if self.zflags is not None:
