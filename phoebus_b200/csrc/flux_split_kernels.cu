@@ -13,6 +13,10 @@
 
 namespace pb {
 
+#ifdef PB_AF_DIAG
+__device__ unsigned g_diag = 0;
+#endif
+
 struct Box { // inclusive cell ranges of one block
   int i0, i1, j0, j1, k0, k1;
   __host__ __device__ int ni() const { return i1 - i0 + 1; }
@@ -116,6 +120,11 @@ __global__ void __launch_bounds__(256, PB_RIEMANN_MINB) riemann_kernel(const pb_
     prim_to_flux<DIR, MHD>(af, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
     prim_to_flux<DIR, MHD>(af, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
     if (af.failed()) {
+#ifdef PB_AF_DIAG
+      if (atomicAdd(&g_diag, 1u) < 24u)
+        printf("riemann bad=%u dir=%d b=%d kji=%d %d %d qL: %g %g %g %g %g | %g %g %g qR: %g %g %g %g %g | %g %g %g\n", af.bad, DIR, b, k, j, i,
+               qL[0], qL[1], qL[2], qL[3], qL[4], qL[5], qL[6], qL[7], qR[0], qR[1], qR[2], qR[3], qR[4], qR[5], qR[6], qR[7]);
+#endif
       ArithExact ax;
       prim_to_flux<DIR, MHD>(ax, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
       prim_to_flux<DIR, MHD>(ax, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);

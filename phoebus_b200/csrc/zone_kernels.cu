@@ -1,5 +1,7 @@
 // One-zone-per-thread tasks over a whole pack: ConservedToPrimitive (robust), its failure fixup,
 // ApplyFloors, PrimitiveToConserved, physical boundary conditions, the CFL estimate.
+#include <cstdlib>
+
 #include "pb_device.cuh"
 #include "pb_host.hpp"
 
@@ -61,7 +63,7 @@ template <bool MHD> struct ZonePtr {
 
 // c2p on one zone with the reference's write pattern: nothing is written when the NaN guard trips,
 // only p.bfield when the root is not bracketed (the reference aborts there; we count it).
-template <bool MHD>
+template <bool MHD, bool FAST>
 PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const ZonePtr<MHD> &z, int ndim,
                             Real *U, Real *P, unsigned long long *err_count) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
@@ -70,7 +72,23 @@ PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const Point
   const Real D0 = U[CRHO], S0 = U[CMOM], S1 = U[CMOM + 1], S2 = U[CMOM + 2], T0 = U[CENG];
   bool unbracketed;
   const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
-  const bool ok = c2p_zone<MHD>(cfg, fc, g, U, P, temp, mu, sig, unbracketed);
+  bool ok;
+  if (FAST) {
+    // deferred-branch divide / sqrt (ArithFast); a zone with an operand outside its exponent range is
+    // solved again from the saved inputs with the compiler's own sequences
+    const Real mu0 = mu;
+    ArithFast af;
+    ok = c2p_zone<MHD>(af, cfg, fc, g, U, P, temp, mu, sig, unbracketed);
+    if (af.failed()) {
+      U[CRHO] = D0, U[CMOM] = S0, U[CMOM + 1] = S1, U[CMOM + 2] = S2, U[CENG] = T0;
+      mu = mu0;
+      ArithExact ax;
+      ok = c2p_zone<MHD>(ax, cfg, fc, g, U, P, temp, mu, sig, unbracketed);
+    }
+  } else {
+    ArithExact ax;
+    ok = c2p_zone<MHD>(ax, cfg, fc, g, U, P, temp, mu, sig, unbracketed);
+  }
   if (nan_in) return false;
   if (unbracketed) {
     if (MHD) {
@@ -204,7 +222,7 @@ PB_DEV bool floors_zone(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom
 #pragma unroll
     for (int n = 0; n < 5; ++n) z.cons[(size_t)n * N] = U[n];
     Real Pn[NP];
-    const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, ndim, U, Pn, nullptr);
+    const bool ok = c2p_zone_global<MHD, false>(cfg, fc, g, z, ndim, U, Pn, nullptr);
     // refresh the local view of the zone from what c2p wrote (it never touches c.bfield)
     load_comps<NP>(z.prim, N, P);
     load_comps<5>(z.cons, N, U);
@@ -317,7 +335,7 @@ struct ZoneCtx { // everything a zone task needs, built from the thread's (b,k,j
 // ref: src/fluid/fluid.cpp:477-517. With zflags != NULL the kernel also records, per zone, whether
 // the c2p failed and whether ApplyFloors will have to touch the zone (one extra byte written instead
 // of a second full pass over the primitives).
-template <bool MHD>
+template <bool MHD, bool FAST>
 __global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
                                                      unsigned long long *err_count, unsigned char *zflags) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
@@ -333,7 +351,7 @@ __global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const
   const ZonePtr<MHD> z(pack, cons, L, b, o);
   Real U[NCn], P[NP];
   load_comps<NCn>(z.cons, L.ncell, U);
-  const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, L.ndim, U, P, err_count);
+  const bool ok = c2p_zone_global<MHD, FAST>(cfg, fc, g, z, L.ndim, U, P, err_count);
   *z.fail = ok ? 1.0 : 0.0;
   if (zflags) {
     unsigned char f = ok ? 0 : ZF_FAIL;
@@ -591,7 +609,7 @@ __global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const 
       const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
       Real U[NCn], P[NP];
       load_comps<NCn>(z.cons, N, U);
-      const bool ok = c2p_zone_global<MHD>(cfg, fc, g, z, L.ndim, U, P, err_count);
+      const bool ok = c2p_zone_global<MHD, false>(cfg, fc, g, z, L.ndim, U, P, err_count);
       *z.fail = ok ? 1.0 : 0.0;
     }
     Real vcon[3] = {z.prim[(size_t)PVEL * N], z.prim[(size_t)(PVEL + 1) * N], z.prim[(size_t)(PVEL + 2) * N]};
@@ -676,8 +694,16 @@ int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const i
   if (reg.n() <= 0) return PB_OK;
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
-  if (cfg->mhd) c2p_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
-  else c2p_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
+  // PB_C2P_ARITH=fast selects the deferred-branch divide/sqrt variant; measured SLOWER here (13.9 vs 12.6 ms
+  // per cycle at 256^3): the solver is bound by divergence and instruction fetch, not by the divide expansion
+  static const bool fast = [] { const char *e = getenv("PB_C2P_ARITH"); return e && e[0] == 'f'; }();
+  if (cfg->mhd) {
+    if (fast) c2p_kernel<true, true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
+    else c2p_kernel<true, false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
+  } else {
+    if (fast) c2p_kernel<false, true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
+    else c2p_kernel<false, false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
+  }
   return check_launch("c2p_kernel");
 }
 int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int mode, unsigned char *zflags, cudaStream_t s) {

@@ -47,6 +47,11 @@ def synthetic_torus(mesh, seed_amp=0.02):
         th = math.pi * X2 + ((1.0 - h) / 2.0) * t.sin(2.0 * math.pi * X2)
         s = t.sin(th).abs()
         tor = t.exp(-((r - r0) / w) ** 2) * s ** 8
+        # compact support, as in the reference pgen: outside the torus surface the atmosphere is at rest and
+        # unmagnetised (v = 0, B = 0 exactly; ref: src/pgen/torus.cpp:246-262 atmosphere branch, and
+        # A_phi = max(rho/rho_max - 0.2, 0), torus.cpp:330-352) instead of Gaussian tails down to denormals
+        tor_v = t.where(tor > 1.0e-3, tor, t.zeros_like(tor))
+        tor_b = t.where(tor > 0.2, tor - 0.2, t.zeros_like(tor))
         wig = 1.0 + seed_amp * t.sin(3.0 * X3 + 5.0 * X1) * t.cos(7.0 * th)
         rho = 1.0e-5 * r ** -1.5 + tor * wig
         u = kappa * rho ** gam / (gam - 1.0) + 1.0e-7 * r ** -2.5
@@ -55,12 +60,12 @@ def synthetic_torus(mesh, seed_amp=0.02):
         prim[0] = rho.expand(shape)
         prim[1] = 0.0
         prim[2] = 0.0
-        prim[3] = (0.5 * tor * r ** -1.5).expand(shape)      # rotation about the axis (x3 = phi)
+        prim[3] = (0.5 * tor_v * r ** -1.5).expand(shape)      # rotation about the axis (x3 = phi)
         prim[4] = u.expand(shape)
         if p.mhd:
             b0 = 2.0e-3
-            prim[5] = (b0 * tor * t.cos(th) / r).expand(shape)
-            prim[6] = (b0 * tor * s / (r * r)).expand(shape)
+            prim[5] = (b0 * tor_b * t.cos(th) / r).expand(shape)
+            prim[6] = (b0 * tor_b * s / (r * r)).expand(shape)
             prim[7] = 0.0
         prim[mesh.nprim - 2] = ((gam - 1.0) * u).expand(shape)
         prim[mesh.nprim - 1] = gam
