@@ -372,15 +372,8 @@ __global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const
 // MODE 1 / 2: driven by the zone flags (post-c2p pass / stale-prim pass of region 7); the zone's
 // floor flag is refreshed because the fixup rewrites its primitives.
 template <bool MHD, int MODE>
-__global__ void __launch_bounds__(128, 4) c2p_fixup_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
-                                                           unsigned char *zflags) {
-  const Lay L(cfg);
-  int b, k, j, i;
-  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
-  const int o = L.idx(k, j, i);
-  if (MODE != 0) {
-    if (!(zflags[(size_t)b * L.ncell + o] & ZF_FAIL)) return;
-  }
+PB_DEV void fixup_body(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, unsigned char *zflags, const Lay &L, int b, int k,
+                       int j, int i, int o) {
   const ZonePtr<MHD> z(pack, cons, L, b, o);
   if (MODE == 0 && *z.fail != 0.0) return;
   const pb_block_t &blk = pack.blocks[b];
@@ -400,24 +393,64 @@ __global__ void __launch_bounds__(128, 4) c2p_fixup_kernel(const pb_pack_t pack,
     zflags[(size_t)b * L.ncell + o] = f;
   }
 }
+template <bool MHD, int MODE>
+__global__ void __launch_bounds__(128, 4) c2p_fixup_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                                                           unsigned char *zflags) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  if (MODE != 0) {
+    if (!(zflags[(size_t)b * L.ncell + o] & ZF_FAIL)) return;
+  }
+  fixup_body<MHD, MODE>(pack, cfg, cons, zflags, L, b, k, j, i, o);
+}
+
+// Flag-driven passes touch << 1 % of the zones: a thread reads 16 flag bytes at once (one uint4) and
+// only then visits the flagged zones, so the pass costs ncell/16 threads instead of ncell.
+constexpr int FLAG_VEC = 16;
+PB_DEV bool flagged_cells(const unsigned char *zflags, long long nvec_total, unsigned char bit, long long &base, unsigned &mask) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nvec_total) return false;
+  const uint4 w = __ldg(reinterpret_cast<const uint4 *>(zflags) + t);
+  const unsigned rep = 0x01010101u * bit;
+  if (((w.x | w.y | w.z | w.w) & rep) == 0) return false;
+  const unsigned words[4] = {w.x, w.y, w.z, w.w};
+  mask = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if ((words[q] >> (8 * c)) & bit) mask |= 1u << (4 * q + c);
+  base = t * FLAG_VEC;
+  return true;
+}
+template <bool MHD, int MODE>
+__global__ void __launch_bounds__(128, 4) c2p_fixup_packed_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons,
+                                                                  const Region reg, unsigned char *zflags) {
+  const Lay L(cfg);
+  long long base;
+  unsigned mask;
+  if (!flagged_cells(zflags, (long long)pack.nblocks * L.ncell / FLAG_VEC, ZF_FAIL, base, mask)) return;
+  const int b = (int)(base / L.ncell);
+  const int o0 = (int)(base - (long long)b * L.ncell);
+  for (int c = 0; c < FLAG_VEC; ++c) {
+    if (!(mask >> c & 1u)) continue;
+    const int o = o0 + c;
+    const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
+    if (i < reg.i0 || i > reg.i1 || j < reg.j0 || j > reg.j1 || k < reg.k0 || k > reg.k1) continue;
+    fixup_body<MHD, MODE>(pack, cfg, cons, zflags, L, b, k, j, i, o);
+  }
+}
 
 // ------------------------------------------------------------------ ApplyFloors
 // MODE 0: full scan (the task as the reference runs it). MODE 1: zones flagged ZF_FLOOR after the
 // entire-domain c2p; leaves ZF_STALE = "floors would fire again on the final primitives".
 // MODE 2: zones flagged ZF_STALE (region 7, stale primitives), ghost cons formed lazily.
 template <bool MHD, int MODE>
-__global__ void __launch_bounds__(128, 4) floors_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
-                                                        unsigned long long *counters, unsigned char *zflags, const LazyGhost lazy) {
+PB_DEV void floors_body(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, unsigned long long *counters, unsigned char *zflags,
+                        const LazyGhost &lazy, const Lay &L, int b, int k, int j, int i, int o, unsigned char f) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
-  const Lay L(cfg);
-  int b, k, j, i;
-  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
-  const int o = L.idx(k, j, i);
-  unsigned char f = 0;
-  if (MODE != 0) {
-    f = zflags[(size_t)b * L.ncell + o];
-    if (!(f & (MODE == 1 ? ZF_FLOOR : ZF_STALE))) return;
-  }
   const pb_block_t &blk = pack.blocks[b];
   const ZonePtr<MHD> z(pack, cons, L, b, o);
   const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
@@ -437,6 +470,37 @@ __global__ void __launch_bounds__(128, 4) floors_kernel(const pb_pack_t pack, co
     f &= ~(ZF_FLOOR | ZF_STALE);
     if (floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_STALE;
     zflags[(size_t)b * L.ncell + o] = f;
+  }
+}
+template <bool MHD, int MODE>
+__global__ void __launch_bounds__(128, 4) floors_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                                                        unsigned long long *counters, unsigned char *zflags, const LazyGhost lazy) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  const int o = L.idx(k, j, i);
+  unsigned char f = 0;
+  if (MODE != 0) {
+    f = zflags[(size_t)b * L.ncell + o];
+    if (!(f & (MODE == 1 ? ZF_FLOOR : ZF_STALE))) return;
+  }
+  floors_body<MHD, MODE>(pack, cfg, cons, counters, zflags, lazy, L, b, k, j, i, o, f);
+}
+template <bool MHD, int MODE>
+__global__ void __launch_bounds__(128, 4) floors_packed_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons,
+                                                               unsigned long long *counters, unsigned char *zflags,
+                                                               const LazyGhost lazy) {
+  const Lay L(cfg);
+  long long base;
+  unsigned mask;
+  if (!flagged_cells(zflags, (long long)pack.nblocks * L.ncell / FLAG_VEC, MODE == 1 ? ZF_FLOOR : ZF_STALE, base, mask)) return;
+  const int b = (int)(base / L.ncell);
+  const int o0 = (int)(base - (long long)b * L.ncell);
+  for (int c = 0; c < FLAG_VEC; ++c) { // the whole block is the region (ApplyFloors runs over the entire domain)
+    if (!(mask >> c & 1u)) continue;
+    const int o = o0 + c;
+    const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
+    floors_body<MHD, MODE>(pack, cfg, cons, counters, zflags, lazy, L, b, k, j, i, o, zflags[(size_t)b * L.ncell + o]);
   }
 }
 
@@ -712,6 +776,17 @@ int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int m
   const Region reg = interior(L);
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
+  if (mode != 0 && L.ncell % FLAG_VEC == 0 && (reinterpret_cast<size_t>(zflags) & 15) == 0) {
+    const unsigned gp = grid_for((long long)pack->nblocks * L.ncell / FLAG_VEC, T);
+#define PB_FIXP(M, MODE) c2p_fixup_packed_kernel<M, MODE><<<gp, T, 0, s>>>(*pack, *cfg, cons, reg, zflags)
+    if (cfg->mhd) {
+      if (mode == 1) PB_FIXP(true, 1); else PB_FIXP(true, 2);
+    } else {
+      if (mode == 1) PB_FIXP(false, 1); else PB_FIXP(false, 2);
+    }
+#undef PB_FIXP
+    return check_launch("c2p_fixup_packed_kernel");
+  }
 #define PB_FIX(M, MODE) c2p_fixup_kernel<M, MODE><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, zflags)
   if (cfg->mhd) {
     if (mode == 0) PB_FIX(true, 0); else if (mode == 1) PB_FIX(true, 1); else PB_FIX(true, 2);
@@ -729,6 +804,17 @@ int launch_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, unsi
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
   const LazyGhost lazy{lazy_u0, lazy_ubase, beta};
+  if (mode != 0 && L.ncell % FLAG_VEC == 0 && (reinterpret_cast<size_t>(zflags) & 15) == 0) {
+    const unsigned gp = grid_for((long long)pack->nblocks * L.ncell / FLAG_VEC, T);
+#define PB_FLRP(M, MODE) floors_packed_kernel<M, MODE><<<gp, T, 0, s>>>(*pack, *cfg, cons, counters, zflags, lazy)
+    if (cfg->mhd) {
+      if (mode == 1) PB_FLRP(true, 1); else PB_FLRP(true, 2);
+    } else {
+      if (mode == 1) PB_FLRP(false, 1); else PB_FLRP(false, 2);
+    }
+#undef PB_FLRP
+    return check_launch("floors_packed_kernel");
+  }
 #define PB_FLR(M, MODE) floors_kernel<M, MODE><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, counters, zflags, lazy)
   if (cfg->mhd) {
     if (mode == 0) PB_FLR(true, 0); else if (mode == 1) PB_FLR(true, 1); else PB_FLR(true, 2);
