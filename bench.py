@@ -25,6 +25,10 @@ WEAK_MESH = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512
 # contract-minimum words per zone-stage, 3-D MHD (Nc=8, Nr=10, g=1.953)
 A_TASK_BYTES_PER_ZONE_CYCLE = 2368.0
 G1_WORDS_PER_ZONE_STAGE = 37.0  # CalculateFluxes: R 10 prims, W 3x8 fluxes, W 3 face speeds
+# from the committed ncu captures of this same command (profiles/r01_ncu_recon_riemann.md): dram bytes per launch at
+# 256^3 zones per GPU, and the FP64 pipe utilisation (sm__inst_executed_pipe_fp64 pct of peak sustained active)
+NCU_DRAM_BYTES_PER_LAUNCH = {"recon_kernel": 6.6e9, "flux_kernel": None}
+NCU_FP64_PIPE_PCT = {"recon_kernel": 80.0, "flux_kernel": 50.0}
 
 
 def deck_text(name="torus3d"):
@@ -201,12 +205,25 @@ def run_ours(args):
         return
     peaks, which = measured_peaks()
     peak = float(peaks["hbm_gbs"])
-    # dominant kernel: the fused reconstruction + Riemann kernel (3 launches per stage)
-    ncalls, flux_ms = tsum.get("flux", (0, 0.0))
-    nlaunch = max(1, ncalls * mesh.ndim)
+    # dominant kernel. Two-launch flux path (default): recon_kernel, one launch per direction and stage, timed by
+    # the in-library CUDA events around exactly those launches. Its algorithmic traffic is what the kernel must
+    # move given its task: Nr primitives read, ql + qr (2 Nr words) written per reconstructed cell
+    # ((nx+2)^3 cells per MeshBlock). Fused path (PB_FLUX_MODE=fused): flux_kernel, SURVEY 8(d) G1 bytes.
     zones_rank = mesh.zones()
-    alg_bytes = G1_WORDS_PER_ZONE_STAGE * 8.0 / mesh.ndim * zones_rank  # per launch (one direction)
-    avg_ms = flux_ms / nlaunch
+    if "recon" in tsum:
+        ncalls, k_ms = tsum["recon"]
+        nlaunch = max(1, ncalls)
+        cells = mesh.nblocks
+        for d in range(3):
+            cells *= (mesh.nx[d] + 2) if d < mesh.ndim else 1
+        alg_bytes = 3.0 * mesh.nprim * 8.0 * cells
+        kname = "recon_kernel<DIR,weno5z,10 prims> (reconstruction, one launch per direction; riemann_kernel follows)"
+    else:
+        ncalls, k_ms = tsum.get("flux", (0, 0.0))
+        nlaunch = max(1, ncalls * mesh.ndim)
+        alg_bytes = G1_WORDS_PER_ZONE_STAGE * 8.0 / mesh.ndim * zones_rank  # per launch (one direction)
+        kname = "flux_kernel<DIR,weno5z,mhd> (fused reconstruction + Riemann, one launch per direction)"
+    avg_ms = k_ms / nlaunch
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     out = {
         "metric": "zone-cycles/s", "value": value, "unit": "zone-cycles/s", "n_gpus": world, "steps": args.steps,
@@ -217,9 +234,10 @@ def run_ours(args):
                    "recon": fp.recon, "riemann": fp.riemann, "integrator": "rk2", "geometry": "fmks a=0.9375 (host-tabulated, axisymmetric)",
                    "parallelism": "meshblock bricks %s" % "x".join(map(str, mesh.rgrid)),
                    "l2": "working set %.1f GB per GPU >> 126 MB L2" % (mesh.bytes_allocated() / 1e9)},
-        "roofline": {"bound": "hbm", "kernel": "flux_kernel<DIR,weno5z,mhd> (fused reconstruction + Riemann, one launch per direction)",
+        "roofline": {"bound": "hbm", "kernel": kname, "co_bound": "fp64 pipe (no FMA contraction: bit parity with the reference)",
+                     "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(kname.split("<")[0]), "traffic_source": "profiles/r01_ncu_recon_riemann.md",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                     "traffic": None, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(kname.split("<")[0]), "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "step_frac_of_hbm_roofline": value / world * A_TASK_BYTES_PER_ZONE_CYCLE / (peak * 1e9)},
         "breakdown_ms_per_step": {k: v[1] / args.steps for k, v in sorted(tsum.items())},
         "gpu_launches": launches,

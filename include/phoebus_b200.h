@@ -228,7 +228,9 @@ int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1,
 #define PB_TASK_BCS 6
 #define PB_TASK_C2P 7
 #define PB_TASK_FIXUP_FLOORS 8
-#define PB_NTASK 9
+#define PB_TASK_RECON 9    /* nested in PB_TASK_FLUX: the recon_kernel launches of the two-launch flux path */
+#define PB_TASK_RIEMANN 10 /* nested in PB_TASK_FLUX: the riemann_kernel launches */
+#define PB_NTASK 11
 int pb_profile_enable(int on);
 /* Device self-test of the library's deferred-branch FP64 divide / reciprocal / square root against
  * IEEE a/b, 1.0/x, sqrt(x) on n pseudo-random operand pairs with exponents in +-exponent_span.

@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get("PHOEBUS_B200_LIB") or os.path.join(HERE, "libphoebus_
 PB_NGLOC, PB_NGDER = 21, 33
 PB_GEOM_WORDS = 4 * PB_NGLOC + PB_NGDER
 PB_NBR_NONE, PB_NBR_REMOTE = -1, -2
-TASK_NAMES = ("flux", "ct_fix", "source", "update", "stale_fixup_floors", "halo", "bcs", "c2p", "fixup_floors")
+TASK_NAMES = ("flux", "ct_fix", "source", "update", "stale_fixup_floors", "halo", "bcs", "c2p", "fixup_floors",
+              "recon", "riemann")  # the last two are nested inside "flux"
 
 
 class PbBlock(C.Structure):

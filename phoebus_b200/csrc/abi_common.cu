@@ -116,6 +116,23 @@ struct ProfScope {
 };
 } // namespace pb
 
+namespace pb {
+void prof_begin(int id, cudaStream_t s) {
+  if (g_prof.on) {
+    cudaEvent_t e = g_prof.get();
+    cudaEventRecord(e, s);
+    g_prof.ev[id][0].push_back(e);
+  }
+}
+void prof_end(int id, cudaStream_t s) {
+  if (g_prof.on) {
+    cudaEvent_t e = g_prof.get();
+    cudaEventRecord(e, s);
+    g_prof.ev[id][1].push_back(e);
+  }
+}
+} // namespace pb
+
 extern "C" int pb_profile_enable(int on) {
   pb::g_prof.on = on != 0;
   return PB_OK;

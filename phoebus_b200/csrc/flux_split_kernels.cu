@@ -168,10 +168,14 @@ static int launch_dir_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStre
   Real *ql = pack.recon_lr, *qr = pack.recon_lr + (size_t)pack.nblocks * NP * L.ncell;
   const int T = 256;
   const long long n1 = rc.n() * pack.nblocks, n2 = rf.n() * pack.nblocks;
+  prof_begin(PB_TASK_RECON, s);
   recon_kernel<DIR, RECON, NP><<<(unsigned)((n1 + T - 1) / T), T, 0, s>>>(pack.prim, ql, qr, cfg, rc, pack.nblocks);
+  prof_end(PB_TASK_RECON, s);
   int rcode = check_launch("recon_kernel");
   if (rcode) return rcode;
+  prof_begin(PB_TASK_RIEMANN, s);
   riemann_kernel<DIR, MHD><<<(unsigned)((n2 + T - 1) / T), T, 0, s>>>(pack, cfg, rf, ql, qr);
+  prof_end(PB_TASK_RIEMANN, s);
   return check_launch("riemann_kernel");
 }
 

@@ -19,5 +19,9 @@ int flux_threads_target();
 int zone_threads();
 bool flux_split_enabled(); // PB_FLUX_MODE=fused|split (default split when the pack carries ql/qr scratch)
 
+// per-task device timing (pb_profile_enable): events on the launching stream, no-ops when off
+void prof_begin(int task, cudaStream_t s);
+void prof_end(int task, cudaStream_t s);
+
 } // namespace pb
 #endif

@@ -113,7 +113,9 @@ class FluidDriver:
     @property
     def LAUNCHES_PER_STAGE(self):
         m = self.m
-        n = m.ndim + 1 + 1 + 1 + 1
+        import os
+        split = m.recon_lr is not None and not os.environ.get("PB_FLUX_MODE", "split").startswith("f")
+        n = m.ndim * (2 if split else 1) + 1 + 1 + 1 + 1
         if m.gsrc is not None:
             n += 1
         if m.zflags is None:

@@ -26,10 +26,20 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in _lib.lib().pb_version()
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors vs the C header, as the C compiler lays the structs out"""
+    import subprocess
     from phoebus_b200 import _lib
-    assert C.sizeof(_lib.PbBlock) == 192
-    assert C.sizeof(_lib.PbPack) == 16 * 8
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "phoebus_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(pb_block_t), sizeof(pb_cfg_t), sizeof(pb_pack_t),'
+                   ' offsetof(pb_pack_t, recon_lr), offsetof(pb_cfg_t, ox1_inflow_check), offsetof(pb_block_t, nbr)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_lib.PbBlock), C.sizeof(_lib.PbCfg), C.sizeof(_lib.PbPack), _lib.PbPack.recon_lr.offset,
+            _lib.PbCfg.ox1_inflow_check.offset, _lib.PbBlock.nbr.offset]
+    assert got == want, (got, want)
 
 
 @pytest.mark.parametrize("name", CASES)
