@@ -240,6 +240,9 @@ int pb_selftest_arith(long long n, unsigned long long seed, int exponent_span, u
                       void *stream);
 int pb_profile_read(double ms[PB_NTASK], int calls[PB_NTASK]);
 
+/* Faces that the fast arithmetic rejected and riemann_redo_kernel recomputed with the compiler's divide / sqrt,
+ * accumulated since the library was loaded (synchronises the device). */
+unsigned long long pb_arith_redo_count(void);
 /* Same idea one level up: riemann.hpp's prim_to_flux (face state -> U, F, v+-) evaluated with the
  * deferred-branch arithmetic and with the compiler's, on n synthetic MHD face states (flat != 0:
  * Minkowski metric; else a random metric). counts_dev[0] = states whose outputs differ in any bit,

@@ -264,7 +264,10 @@ template <bool MHD> static int launch_recon(const pb_pack_t &pack, const pb_cfg_
 
 namespace pb {
 int calculate_fluxes_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s); // flux_split_kernels.cu
+unsigned long long redo_total_host();
 }
+
+extern "C" unsigned long long pb_arith_redo_count(void) { return pb::redo_total_host(); }
 
 extern "C" int pb_calculate_fluxes(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream) {
   using namespace pb;

@@ -78,13 +78,12 @@ __global__ void __launch_bounds__(256, PB_RECON_MINB) recon_kernel(const Real *_
   }
 }
 
-template <int DIR, bool MHD>
-__global__ void __launch_bounds__(256, PB_RIEMANN_MINB) riemann_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Box reg,
-                                                                       const Real *__restrict__ ql, const Real *__restrict__ qr) {
+// One face: load both states and the face geometry, prim_to_flux on each, LLF / HLL, store.
+// Returns the arithmetic policy's failure flag (always false for ArithExact).
+template <int DIR, bool MHD, class AR>
+PB_DEV bool riemann_face(const pb_pack_t &pack, const pb_cfg_t &cfg, const Lay &L, const Real *__restrict__ ql,
+                         const Real *__restrict__ qr, int b, int k, int j, int i) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
-  const Lay L(cfg);
-  int b, k, j, i;
-  if (!cell_of_thread(reg, pack.nblocks, b, k, j, i)) return;
   const int o = L.idx(k, j, i);
   const pb_block_t &blk = pack.blocks[b];
   Real qL[NP], qR[NP];
@@ -115,21 +114,9 @@ __global__ void __launch_bounds__(256, PB_RIEMANN_MINB) riemann_kernel(const pb_
   fc.x3 = (DIR == 3) ? Xf(blk, 2, k) : Xc(blk, 2, k);
 
   Real Ul[NCn], Fl[NCn], Ur[NCn], Fr[NCn], vml, vpl, vmr, vpr;
-  {
-    ArithFast af;
-    prim_to_flux<DIR, MHD>(af, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
-    prim_to_flux<DIR, MHD>(af, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
-    if (af.failed()) {
-#ifdef PB_AF_DIAG
-      if (atomicAdd(&g_diag, 1u) < 24u)
-        printf("riemann bad=%u dir=%d b=%d kji=%d %d %d qL: %g %g %g %g %g | %g %g %g qR: %g %g %g %g %g | %g %g %g\n", af.bad, DIR, b, k, j, i,
-               qL[0], qL[1], qL[2], qL[3], qL[4], qL[5], qL[6], qL[7], qR[0], qR[1], qR[2], qR[3], qR[4], qR[5], qR[6], qR[7]);
-#endif
-      ArithExact ax;
-      prim_to_flux<DIR, MHD>(ax, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
-      prim_to_flux<DIR, MHD>(ax, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
-    }
-  }
+  AR ar;
+  prim_to_flux<DIR, MHD>(ar, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
+  prim_to_flux<DIR, MHD>(ar, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
   Real *fl = pack.flux + ((size_t)b * L.ndim + (DIR - 1)) * NCn * L.ncell + o;
   Real speed;
   if (cfg.riemann == 0) { // llf, ref: riemann.hpp:256-276
@@ -149,6 +136,79 @@ __global__ void __launch_bounds__(256, PB_RIEMANN_MINB) riemann_kernel(const pb_
     speed = dmax(-cl, cr);
   }
   pack.fsig[((size_t)b * L.ndim + (DIR - 1)) * L.ncell + o] = speed;
+  return ar.failed();
+}
+
+// Faces whose operands fall outside the fast divide's exponent range are not redone in place (keeping
+// both code paths in one kernel costs 300 B of spills and doubles its size): their linear index goes
+// to a device queue and riemann_redo_kernel recomputes exactly those faces with the compiler's a/b,
+// 1/x, sqrt right after, on the same stream, overwriting what the fast pass stored.
+struct RedoQueue {
+  unsigned *count; // [0] entries of this launch, [1] unused
+  unsigned *list;
+  unsigned long long *total; // accumulated over the life of the library (diagnostics)
+};
+
+PB_DEV void face_of_index(const Box &r, long long t, int &b, int &k, int &j, int &i) {
+  const long long nreg = r.n();
+  b = (int)(t / nreg);
+  int rem = (int)(t - (long long)b * nreg);
+  const int q = rem / r.ni();
+  i = r.i0 + (rem - q * r.ni());
+  const int q2 = q / r.nj();
+  j = r.j0 + (q - q2 * r.nj());
+  k = r.k0 + q2;
+}
+
+template <int DIR, bool MHD>
+__global__ void __launch_bounds__(256, PB_RIEMANN_MINB) riemann_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Box reg,
+                                                                       const Real *__restrict__ ql, const Real *__restrict__ qr,
+                                                                       const RedoQueue rq) {
+  const Lay L(cfg);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= reg.n() * pack.nblocks) return;
+  int b, k, j, i;
+  face_of_index(reg, t, b, k, j, i);
+  if (riemann_face<DIR, MHD, ArithFast>(pack, cfg, L, ql, qr, b, k, j, i)) rq.list[atomicAdd(rq.count, 1u)] = (unsigned)t;
+}
+
+template <int DIR, bool MHD>
+__global__ void __launch_bounds__(128) riemann_redo_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Box reg,
+                                                           const Real *__restrict__ ql, const Real *__restrict__ qr,
+                                                           const RedoQueue rq) {
+  const Lay L(cfg);
+  const unsigned n = *rq.count;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(rq.total, (unsigned long long)n);
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    int b, k, j, i;
+    face_of_index(reg, (long long)rq.list[e], b, k, j, i);
+    riemann_face<DIR, MHD, ArithExact>(pack, cfg, L, ql, qr, b, k, j, i);
+  }
+}
+
+// library-owned workspace for the queue (grown on demand, never inside a timed region after warm-up)
+static RedoQueue g_rq = {nullptr, nullptr, nullptr};
+static size_t g_rq_cap = 0;
+static int redo_queue(size_t entries, RedoQueue &out) {
+  if (!g_rq.count) {
+    if (cudaMalloc(&g_rq.count, 2 * sizeof(unsigned) + sizeof(unsigned long long) + 8) != cudaSuccess)
+      return set_cuda_error(cudaGetLastError(), "redo queue counters");
+    cudaMemset(g_rq.count, 0, 2 * sizeof(unsigned) + sizeof(unsigned long long) + 8);
+    g_rq.total = reinterpret_cast<unsigned long long *>(g_rq.count + 2);
+  }
+  if (entries > g_rq_cap) {
+    if (g_rq.list) cudaFree(g_rq.list);
+    g_rq.list = nullptr;
+    if (cudaMalloc(&g_rq.list, entries * sizeof(unsigned)) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "redo queue");
+    g_rq_cap = entries;
+  }
+  out = g_rq;
+  return PB_OK;
+}
+unsigned long long redo_total_host() {
+  unsigned long long v = 0;
+  if (g_rq.total) cudaMemcpy(&v, g_rq.total, sizeof v, cudaMemcpyDeviceToHost);
+  return v;
 }
 
 template <int DIR, int RECON, bool MHD>
@@ -173,8 +233,13 @@ static int launch_dir_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStre
   prof_end(PB_TASK_RECON, s);
   int rcode = check_launch("recon_kernel");
   if (rcode) return rcode;
+  if (n2 >= (1ll << 32)) return set_error(PB_EINVAL, "pack too large for the 32-bit redo queue");
+  RedoQueue rq;
+  if ((rcode = redo_queue((size_t)n2, rq))) return rcode;
   prof_begin(PB_TASK_RIEMANN, s);
-  riemann_kernel<DIR, MHD><<<(unsigned)((n2 + T - 1) / T), T, 0, s>>>(pack, cfg, rf, ql, qr);
+  cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
+  riemann_kernel<DIR, MHD><<<(unsigned)((n2 + T - 1) / T), T, 0, s>>>(pack, cfg, rf, ql, qr, rq);
+  riemann_redo_kernel<DIR, MHD><<<148 * 4, 128, 0, s>>>(pack, cfg, rf, ql, qr, rq);
   prof_end(PB_TASK_RIEMANN, s);
   return check_launch("riemann_kernel");
 }
