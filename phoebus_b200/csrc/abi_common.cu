@@ -117,6 +117,31 @@ struct ProfScope {
 } // namespace pb
 
 namespace pb {
+static RedoQueue g_rq = {nullptr, nullptr, nullptr};
+static size_t g_rq_cap = 0;
+int redo_queue(size_t entries, RedoQueue &out) {
+  if (!g_rq.count) {
+    if (cudaMalloc(&g_rq.count, 2 * sizeof(unsigned) + sizeof(unsigned long long) + 8) != cudaSuccess)
+      return set_cuda_error(cudaGetLastError(), "redo queue counters");
+    cudaMemset(g_rq.count, 0, 2 * sizeof(unsigned) + sizeof(unsigned long long) + 8);
+    g_rq.total = reinterpret_cast<unsigned long long *>(g_rq.count + 2);
+  }
+  if (entries > g_rq_cap) {
+    cudaDeviceSynchronize(); // an earlier launch may still be reading the old list
+    if (g_rq.list) cudaFree(g_rq.list);
+    g_rq.list = nullptr;
+    if (cudaMalloc(&g_rq.list, entries * sizeof(unsigned)) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "redo queue");
+    g_rq_cap = entries;
+  }
+  out = g_rq;
+  return PB_OK;
+}
+unsigned long long redo_total_host() {
+  unsigned long long v = 0;
+  if (g_rq.total) cudaMemcpy(&v, g_rq.total, sizeof v, cudaMemcpyDeviceToHost);
+  return v;
+}
+
 void prof_begin(int id, cudaStream_t s) {
   if (g_prof.on) {
     cudaEvent_t e = g_prof.get();

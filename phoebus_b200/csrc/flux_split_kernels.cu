@@ -142,13 +142,7 @@ PB_DEV bool riemann_face(const pb_pack_t &pack, const pb_cfg_t &cfg, const Lay &
 // Faces whose operands fall outside the fast divide's exponent range are not redone in place (keeping
 // both code paths in one kernel costs 300 B of spills and doubles its size): their linear index goes
 // to a device queue and riemann_redo_kernel recomputes exactly those faces with the compiler's a/b,
-// 1/x, sqrt right after, on the same stream, overwriting what the fast pass stored.
-struct RedoQueue {
-  unsigned *count; // [0] entries of this launch, [1] unused
-  unsigned *list;
-  unsigned long long *total; // accumulated over the life of the library (diagnostics)
-};
-
+// 1/x, sqrt right after, on the same stream, overwriting what the fast pass stored (RedoQueue: pb_host.hpp).
 PB_DEV void face_of_index(const Box &r, long long t, int &b, int &k, int &j, int &i) {
   const long long nreg = r.n();
   b = (int)(t / nreg);
@@ -184,31 +178,6 @@ __global__ void __launch_bounds__(128) riemann_redo_kernel(const pb_pack_t pack,
     face_of_index(reg, (long long)rq.list[e], b, k, j, i);
     riemann_face<DIR, MHD, ArithExact>(pack, cfg, L, ql, qr, b, k, j, i);
   }
-}
-
-// library-owned workspace for the queue (grown on demand, never inside a timed region after warm-up)
-static RedoQueue g_rq = {nullptr, nullptr, nullptr};
-static size_t g_rq_cap = 0;
-static int redo_queue(size_t entries, RedoQueue &out) {
-  if (!g_rq.count) {
-    if (cudaMalloc(&g_rq.count, 2 * sizeof(unsigned) + sizeof(unsigned long long) + 8) != cudaSuccess)
-      return set_cuda_error(cudaGetLastError(), "redo queue counters");
-    cudaMemset(g_rq.count, 0, 2 * sizeof(unsigned) + sizeof(unsigned long long) + 8);
-    g_rq.total = reinterpret_cast<unsigned long long *>(g_rq.count + 2);
-  }
-  if (entries > g_rq_cap) {
-    if (g_rq.list) cudaFree(g_rq.list);
-    g_rq.list = nullptr;
-    if (cudaMalloc(&g_rq.list, entries * sizeof(unsigned)) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "redo queue");
-    g_rq_cap = entries;
-  }
-  out = g_rq;
-  return PB_OK;
-}
-unsigned long long redo_total_host() {
-  unsigned long long v = 0;
-  if (g_rq.total) cudaMemcpy(&v, g_rq.total, sizeof v, cudaMemcpyDeviceToHost);
-  return v;
 }
 
 template <int DIR, int RECON, bool MHD>

@@ -19,6 +19,18 @@ int flux_threads_target();
 int zone_threads();
 bool flux_split_enabled(); // PB_FLUX_MODE=fused|split (default split when the pack carries ql/qr scratch)
 
+// Device queue of work items (linear thread indices) that the deferred-branch arithmetic (ArithFast, pb_device.cuh)
+// rejected; a *_redo_kernel recomputes exactly those items with the compiler's divide / sqrt right after, on the same
+// stream. Library-owned workspace, grown on demand (first call / larger pack), shared by all users because every use
+// is stream-ordered: memset count -> fast kernel -> redo kernel.
+struct RedoQueue {
+  unsigned *count;           // entries appended by the current launch
+  unsigned *list;            // linear thread index of each rejected item
+  unsigned long long *total; // accumulated over the life of the library (diagnostics: pb_arith_redo_count)
+};
+int redo_queue(size_t entries, RedoQueue &out);
+unsigned long long redo_total_host();
+
 // per-task device timing (pb_profile_enable): events on the launching stream, no-ops when off
 void prof_begin(int task, cudaStream_t s);
 void prof_end(int task, cudaStream_t s);

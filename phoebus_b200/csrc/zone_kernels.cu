@@ -63,9 +63,12 @@ template <bool MHD> struct ZonePtr {
 
 // c2p on one zone with the reference's write pattern: nothing is written when the NaN guard trips,
 // only p.bfield when the root is not bracketed (the reference aborts there; we count it).
-template <bool MHD, bool FAST>
+// ARITH 0: the compiler's divide / sqrt. 1: ArithFast with an inline exact re-solve. 2: ArithFast only; a zone
+// whose operands leave the fast path's exponent range writes NOTHING and reports `rejected` (the caller queues
+// it for c2p_redo_kernel).
+template <bool MHD, int ARITH>
 PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const ZonePtr<MHD> &z, int ndim,
-                            Real *U, Real *P, unsigned long long *err_count) {
+                            Real *U, Real *P, unsigned long long *err_count, bool *rejected = nullptr) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   Real temp, sig[3];
   Real mu = *z.mu;
@@ -73,7 +76,14 @@ PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const Point
   bool unbracketed;
   const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
   bool ok;
-  if (FAST) {
+  if (ARITH == 2) {
+    ArithFast af;
+    ok = c2p_zone<MHD>(af, cfg, fc, g, U, P, temp, mu, sig, unbracketed);
+    if (af.failed()) {
+      *rejected = true;
+      return false;
+    }
+  } else if (ARITH == 1) {
     // deferred-branch divide / sqrt (ArithFast); a zone with an operand outside its exponent range is
     // solved again from the saved inputs with the compiler's own sequences
     const Real mu0 = mu;
@@ -222,7 +232,7 @@ PB_DEV bool floors_zone(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom
 #pragma unroll
     for (int n = 0; n < 5; ++n) z.cons[(size_t)n * N] = U[n];
     Real Pn[NP];
-    const bool ok = c2p_zone_global<MHD, false>(cfg, fc, g, z, ndim, U, Pn, nullptr);
+    const bool ok = c2p_zone_global<MHD, 0>(cfg, fc, g, z, ndim, U, Pn, nullptr);
     // refresh the local view of the zone from what c2p wrote (it never touches c.bfield)
     load_comps<NP>(z.prim, N, P);
     load_comps<5>(z.cons, N, U);
@@ -335,13 +345,10 @@ struct ZoneCtx { // everything a zone task needs, built from the thread's (b,k,j
 // ref: src/fluid/fluid.cpp:477-517. With zflags != NULL the kernel also records, per zone, whether
 // the c2p failed and whether ApplyFloors will have to touch the zone (one extra byte written instead
 // of a second full pass over the primitives).
-template <bool MHD, bool FAST>
-__global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
-                                                     unsigned long long *err_count, unsigned char *zflags) {
+template <bool MHD, int ARITH>
+PB_DEV bool c2p_thread(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, const Lay &L, int b, int k, int j, int i,
+                       unsigned long long *err_count, unsigned char *zflags) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
-  const Lay L(cfg);
-  int b, k, j, i;
-  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
   const int o = L.idx(k, j, i);
   const pb_block_t &blk = pack.blocks[b];
   const GeomTab gt(cfg, pack.geom, blk.geom_slot);
@@ -351,7 +358,9 @@ __global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const
   const ZonePtr<MHD> z(pack, cons, L, b, o);
   Real U[NCn], P[NP];
   load_comps<NCn>(z.cons, L.ncell, U);
-  const bool ok = c2p_zone_global<MHD, FAST>(cfg, fc, g, z, L.ndim, U, P, err_count);
+  bool rejected = false;
+  const bool ok = c2p_zone_global<MHD, ARITH>(cfg, fc, g, z, L.ndim, U, P, err_count, &rejected);
+  if (ARITH == 2 && rejected) return true;
   *z.fail = ok ? 1.0 : 0.0;
   if (zflags) {
     unsigned char f = ok ? 0 : ZF_FAIL;
@@ -364,6 +373,35 @@ __global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const
       if (floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_FLOOR;
     }
     zflags[(size_t)b * L.ncell + o] = f;
+  }
+  return false;
+}
+
+template <bool MHD, int ARITH>
+__global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                                                     unsigned long long *err_count, unsigned char *zflags, const RedoQueue rq) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  if (c2p_thread<MHD, ARITH>(pack, cfg, cons, L, b, k, j, i, err_count, zflags))
+    rq.list[atomicAdd(rq.count, 1u)] = (unsigned)((long long)blockIdx.x * blockDim.x + threadIdx.x);
+}
+// zones the fast arithmetic rejected, solved with the compiler's divide / sqrt (see RedoQueue, pb_host.hpp)
+template <bool MHD>
+__global__ void __launch_bounds__(128, 4) c2p_redo_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                                                          unsigned long long *err_count, unsigned char *zflags, const RedoQueue rq) {
+  const Lay L(cfg);
+  const unsigned n = *rq.count;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(rq.total, (unsigned long long)n);
+  const long long nreg = reg.n();
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const long long t = rq.list[e];
+    const int b = (int)(t / nreg);
+    int rem = (int)(t % nreg);
+    const int i = reg.i0 + rem % reg.ni();
+    rem /= reg.ni();
+    const int j = reg.j0 + rem % reg.nj(), k = reg.k0 + rem / reg.nj();
+    c2p_thread<MHD, 0>(pack, cfg, cons, L, b, k, j, i, err_count, zflags);
   }
 }
 
@@ -673,7 +711,7 @@ __global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const 
       const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
       Real U[NCn], P[NP];
       load_comps<NCn>(z.cons, N, U);
-      const bool ok = c2p_zone_global<MHD, false>(cfg, fc, g, z, L.ndim, U, P, err_count);
+      const bool ok = c2p_zone_global<MHD, 0>(cfg, fc, g, z, L.ndim, U, P, err_count);
       *z.fail = ok ? 1.0 : 0.0;
     }
     Real vcon[3] = {z.prim[(size_t)PVEL * N], z.prim[(size_t)(PVEL + 1) * N], z.prim[(size_t)(PVEL + 2) * N]};
@@ -758,15 +796,30 @@ int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const i
   if (reg.n() <= 0) return PB_OK;
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
-  // PB_C2P_ARITH=fast selects the deferred-branch divide/sqrt variant; measured SLOWER here (13.9 vs 12.6 ms
-  // per cycle at 256^3): the solver is bound by divergence and instruction fetch, not by the divide expansion
-  static const bool fast = [] { const char *e = getenv("PB_C2P_ARITH"); return e && e[0] == 'f'; }();
+  // PB_C2P_ARITH: queue (default) = ArithFast, rejected zones re-solved by c2p_redo_kernel; exact = the
+  // compiler's divide / sqrt everywhere; inline = ArithFast with the exact re-solve inside the kernel
+  static const int mode = [] {
+    const char *e = getenv("PB_C2P_ARITH");
+    return (e && e[0] == 'e') ? 0 : ((e && e[0] == 'i') ? 1 : 2);
+  }();
+  RedoQueue rq{nullptr, nullptr, nullptr};
+  if (mode == 2) {
+    const long long nthr = reg.n() * pack->nblocks;
+    if (nthr >= (1ll << 32)) return set_error(PB_EINVAL, "pack too large for the 32-bit redo queue");
+    int rc = redo_queue((size_t)nthr, rq);
+    if (rc) return rc;
+    cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
+  }
+#define PB_C2P(M, A) c2p_kernel<M, A><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags, rq)
   if (cfg->mhd) {
-    if (fast) c2p_kernel<true, true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
-    else c2p_kernel<true, false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
+    if (mode == 0) PB_C2P(true, 0); else if (mode == 1) PB_C2P(true, 1); else PB_C2P(true, 2);
   } else {
-    if (fast) c2p_kernel<false, true><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
-    else c2p_kernel<false, false><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags);
+    if (mode == 0) PB_C2P(false, 0); else if (mode == 1) PB_C2P(false, 1); else PB_C2P(false, 2);
+  }
+#undef PB_C2P
+  if (mode == 2) {
+    if (cfg->mhd) c2p_redo_kernel<true><<<148 * 4, 128, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags, rq);
+    else c2p_redo_kernel<false><<<148 * 4, 128, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags, rq);
   }
   return check_launch("c2p_kernel");
 }
