@@ -147,6 +147,7 @@ def run_ours(args):
         sampler.start()
     drv.enable_profile(True)
     launches0 = drv.launches
+    redo0 = drv.L.pb_arith_redo_count()
     mesh.counters.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -164,10 +165,12 @@ def run_ours(args):
     launches = drv.launches - launches0
     tsum = drv.timer_summary()
     drv.enable_profile(False)
+    redo = float(drv.L.pb_arith_redo_count() - redo0)
     counters = mesh.counters.clone()
     nfail = (mesh.fail == 0).sum()
     finite = torch.isfinite(mesh.cons["base"]).all() & torch.isfinite(mesh.prim).all()
     stats = torch.stack([counters[0], counters[1], counters[2], nfail, (~finite).to(torch.int64)]).to(torch.float64)
+    stats = torch.cat([stats, torch.tensor([redo], dtype=torch.float64, device=device)])
     if world > 1:
         dist.all_reduce(stats)
     value = zones_total * args.steps / (ms_total * 1e-3)
@@ -242,7 +245,8 @@ def run_ours(args):
         "breakdown_ms_per_step": {k: v[1] / args.steps for k, v in sorted(tsum.items())},
         "gpu_launches": launches,
         "zone_stats": {"floors": int(stats[0]), "ceilings": int(stats[1]), "floor_c2p_fail": int(stats[2]),
-                       "failed_zones_now": int(stats[3]), "nonfinite": int(stats[4])},
+                       "failed_zones_now": int(stats[3]), "nonfinite": int(stats[4]),
+                       "arith_redo_items": int(stats[5])},
         "clocks": sampler.summary(),
     }
     if e2e:

@@ -240,7 +240,13 @@ int pb_selftest_arith(long long n, unsigned long long seed, int exponent_span, u
                       void *stream);
 int pb_profile_read(double ms[PB_NTASK], int calls[PB_NTASK]);
 
-/* Faces that the fast arithmetic rejected and riemann_redo_kernel recomputed with the compiler's divide / sqrt,
+/* Run-time options of the library (initial values from the environment variables in parentheses):
+ *   "flux_split" 1|0  (PB_FLUX_MODE=split|fused)  two-launch flux path when the pack has recon_lr, else the fused kernel
+ *   "c2p_arith"  2|0|1 (PB_C2P_ARITH=queue|exact|inline) con2prim arithmetic: ArithFast + redo queue, the compiler's
+ *                divide / sqrt, ArithFast with an inline exact re-solve. All settings produce identical bits. */
+int pb_set_option(const char *key, int value);
+int pb_get_option(const char *key);
+/* Faces / zones that the fast arithmetic rejected and riemann_redo_kernel / c2p_redo_kernel recomputed with the compiler's divide / sqrt,
  * accumulated since the library was loaded (synchronises the device). */
 unsigned long long pb_arith_redo_count(void);
 /* Same idea one level up: riemann.hpp's prim_to_flux (face state -> U, F, v+-) evaluated with the

@@ -84,6 +84,8 @@ SYMBOLS = {
     "pb_profile_read": (C.c_int, [_P, _P]),
     "pb_selftest_arith": (C.c_int, [C.c_longlong, C.c_ulonglong, C.c_int, _P, _P]),
     "pb_arith_redo_count": (C.c_ulonglong, []),
+    "pb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "pb_get_option": (C.c_int, [C.c_char_p]),
     "pb_selftest_riemann": (C.c_int, [C.c_longlong, C.c_ulonglong, _CFG, C.c_int, _P, _P, _P]),
     "pb_rk_stage": (C.c_int, [_PACK, _CFG, _P, _P, _P, C.c_double, C.c_double, _P, _P]),
     "pb_rk_stage_pre": (C.c_int, [_PACK, _CFG, _P, _P, _P, C.c_double, C.c_double, _P, _P]),

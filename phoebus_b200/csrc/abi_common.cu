@@ -48,13 +48,18 @@ int flux_threads_target() {
   static int v = env_int("PB_FLUX_THREADS", 272);
   return v;
 }
-bool flux_split_enabled() { // PB_FLUX_MODE=fused forces the one-launch kernel even when the pack has ql/qr scratch
-  static int v = [] {
-    const char *e = getenv("PB_FLUX_MODE");
-    return (e && e[0] == 'f') ? 0 : 1;
-  }();
-  return v != 0;
-}
+// run-time options (pb_set_option); initial values from the environment: PB_FLUX_MODE=fused|split,
+// PB_C2P_ARITH=queue|exact|inline
+static int g_flux_split = [] {
+  const char *e = getenv("PB_FLUX_MODE");
+  return (e && e[0] == 'f') ? 0 : 1;
+}();
+static int g_c2p_arith = [] {
+  const char *e = getenv("PB_C2P_ARITH");
+  return (e && e[0] == 'e') ? 0 : ((e && e[0] == 'i') ? 1 : 2);
+}();
+bool flux_split_enabled() { return g_flux_split != 0; }
+int c2p_arith_mode() { return g_c2p_arith; }
 int zone_threads() {
   static int v = env_int("PB_ZONE_THREADS", 128);
   return v > 128 ? 128 : v; // zone kernels are compiled with __launch_bounds__(128, n)
@@ -157,6 +162,18 @@ void prof_end(int id, cudaStream_t s) {
   }
 }
 } // namespace pb
+
+extern "C" int pb_set_option(const char *key, int value) {
+  if (key && !strcmp(key, "flux_split")) g_flux_split = value != 0;
+  else if (key && !strcmp(key, "c2p_arith") && value >= 0 && value <= 2) g_c2p_arith = value;
+  else return set_error(PB_EINVAL, "pb_set_option: unknown key or value");
+  return PB_OK;
+}
+extern "C" int pb_get_option(const char *key) {
+  if (key && !strcmp(key, "flux_split")) return g_flux_split;
+  if (key && !strcmp(key, "c2p_arith")) return g_c2p_arith;
+  return set_error(PB_EINVAL, "pb_get_option: unknown key");
+}
 
 extern "C" int pb_profile_enable(int on) {
   pb::g_prof.on = on != 0;

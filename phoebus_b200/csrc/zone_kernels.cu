@@ -798,10 +798,7 @@ int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const i
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
   // PB_C2P_ARITH: queue (default) = ArithFast, rejected zones re-solved by c2p_redo_kernel; exact = the
   // compiler's divide / sqrt everywhere; inline = ArithFast with the exact re-solve inside the kernel
-  static const int mode = [] {
-    const char *e = getenv("PB_C2P_ARITH");
-    return (e && e[0] == 'e') ? 0 : ((e && e[0] == 'i') ? 1 : 2);
-  }();
+  const int mode = c2p_arith_mode();
   RedoQueue rq{nullptr, nullptr, nullptr};
   if (mode == 2) {
     const long long nthr = reg.n() * pack->nblocks;

@@ -113,9 +113,11 @@ class FluidDriver:
     @property
     def LAUNCHES_PER_STAGE(self):
         m = self.m
-        import os
-        split = m.recon_lr is not None and not os.environ.get("PB_FLUX_MODE", "split").startswith("f")
-        n = m.ndim * (2 if split else 1) + 1 + 1 + 1 + 1
+        split = m.recon_lr is not None and self.L.pb_get_option(b"flux_split") == 1
+        # flux: recon + riemann + riemann_redo per direction (split) or one fused launch; update; fixup; floors...
+        n = m.ndim * (3 if split else 1) + 1 + 1 + 1 + 1
+        if self.L.pb_get_option(b"c2p_arith") == 2:
+            n += 1  # c2p_redo_kernel
         if m.gsrc is not None:
             n += 1
         if m.zflags is None:

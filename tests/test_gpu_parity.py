@@ -271,3 +271,63 @@ def test_fast_arith_riemann_states_bit_identical(name, flat):
     c = counts.cpu().tolist()
     assert c[0] == 0, (c, first.cpu().tolist())
     assert c[1] < n // 2, c
+
+
+def _tails_state(mesh):
+    """a state full of operands the fast arithmetic must reject: velocities and fields decaying through
+    1e-150 ... denormals ... exact zeros (what Gaussian tails or numerical diffusion fronts look like)"""
+    import torch
+    t = torch
+    dev = mesh.prim.device
+    nb = mesh.nblocks
+    shape = mesh.prim.shape[2:]
+    gi = t.arange(shape[-1], device=dev, dtype=t.float64).view(1, 1, -1)
+    gj = t.arange(shape[-2], device=dev, dtype=t.float64).view(1, -1, 1)
+    gk = t.arange(shape[-3], device=dev, dtype=t.float64).view(-1, 1, 1)
+    for n in range(nb):
+        decay = t.exp(-((gi + 3.0 * gj + 7.0 * gk + 11.0 * n) * 9.0))  # 1 ... 1e-300 ... denormal ... 0
+        p = mesh.prim[n]
+        p[0] = 1.0 + 0.1 * t.sin(gi + gj)
+        p[1] = 0.3 * decay
+        p[2] = -0.2 * decay * decay
+        p[3] = 0.1 * decay
+        p[4] = 0.5 * p[0]
+        if mesh.p.mhd:
+            p[5] = 0.2 * decay
+            p[6] = -0.1 * decay
+            p[7] = 0.05 * decay * decay
+        p[mesh.nprim - 2] = (mesh.p.gamma - 1.0) * p[4]
+        p[mesh.nprim - 1] = mesh.p.gamma
+
+
+@pytest.mark.parametrize("name", ["blast3d", "torus2d"])
+def test_redo_queues_reproduce_exact_arithmetic(name):
+    """operands outside the fast divide's range: the queue + redo kernels (default) must give the bits of the
+    all-exact paths (fused flux kernel with its inline exact fallback; con2prim with the compiler's divide)"""
+    import torch
+    from phoebus_b200 import _lib
+    L = _lib.lib()
+    g, p = load_case(name)
+    results = []
+    redo0 = L.pb_arith_redo_count()
+    try:
+        for flux_split, c2p_arith in ((1, 2), (0, 0)):
+            L.pb_set_option(b"flux_split", flux_split)
+            L.pb_set_option(b"c2p_arith", c2p_arith)
+            mesh, fp = product_mesh(g, device=_dev())
+            _tails_state(mesh)
+            pk, cfg = C.byref(mesh.pack), C.byref(mesh.cfg)
+            I2 = C.c_int * 2
+            ib, jb, kb = I2(0, mesh.ni - 1), I2(0, mesh.nj - 1), I2(0, mesh.nk - 1)
+            base = mesh.cons["base"]
+            _lib.check(L.pb_prim_to_cons(pk, cfg, base.data_ptr(), ib, jb, kb, None), "p2c")
+            _lib.check(L.pb_calculate_fluxes(pk, cfg, None), "flux")
+            _lib.check(L.pb_cons_to_prim(pk, cfg, base.data_ptr(), ib, jb, kb, None), "c2p")
+            torch.cuda.synchronize()
+            results.append({k: _np(getattr(mesh, k)).copy() for k in ("flux", "fsig", "prim", "c2p_mu", "fail", "csig", "temp")})
+    finally:
+        L.pb_set_option(b"flux_split", 1)
+        L.pb_set_option(b"c2p_arith", 2)
+    assert L.pb_arith_redo_count() > redo0, "the test state did not exercise the redo kernels"
+    for k in results[0]:
+        assert np.array_equal(results[0][k], results[1][k], equal_nan=True), k
