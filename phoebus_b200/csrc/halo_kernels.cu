@@ -60,7 +60,15 @@ __global__ void halo_local_kernel(const pb_pack_t pack, const pb_cfg_t cfg, cons
     const int nc = hf.ncomp[f];
     const Real *src = hf.ptr[f] + (size_t)nb * nc * N + so;
     Real *dst = hf.ptr[f] + (size_t)b * nc * N + o;
-    for (int n = 0; n < nc; ++n) dst[(size_t)n * N] = src[(size_t)n * N];
+    int n = 0;
+    for (; n + 4 <= nc; n += 4) { // four independent loads in flight per thread (the copy is latency bound otherwise)
+      const Real v0 = src[(size_t)n * N], v1 = src[(size_t)(n + 1) * N], v2 = src[(size_t)(n + 2) * N], v3 = src[(size_t)(n + 3) * N];
+      dst[(size_t)n * N] = v0;
+      dst[(size_t)(n + 1) * N] = v1;
+      dst[(size_t)(n + 2) * N] = v2;
+      dst[(size_t)(n + 3) * N] = v3;
+    }
+    for (; n < nc; ++n) dst[(size_t)n * N] = src[(size_t)n * N];
   }
 }
 
@@ -80,13 +88,26 @@ __global__ void halo_buffer_kernel(const pb_pack_t pack, const pb_cfg_t cfg, con
   for (int f = 0; f < hf.nfield; ++f) {
     const int nc = hf.ncomp[f];
     Real *fld = hf.ptr[f] + (size_t)b * nc * N;
-    for (int e = threadIdx.x; e < nc * nz; e += blockDim.x) {
-      const int n = e / nz, z = e % nz;
+    // gridDim.y CTAs share one segment; each thread moves all components of its zones, four loads in flight
+    for (int z = blockIdx.y * blockDim.x + threadIdx.x; z < nz; z += gridDim.y * blockDim.x) {
       const int i = i0 + z % ni, j = j0 + (z / ni) % nj, k = k0 + z / (ni * nj);
-      Real *g = fld + (size_t)n * N + L.idx(k, j, i);
-      Real *s = seg + (size_t)(var0 + n) * nz + z;
-      if (PACK) *s = *g;
-      else *g = *s;
+      Real *g = fld + L.idx(k, j, i);
+      Real *s = seg + (size_t)var0 * nz + z;
+      int n = 0;
+      for (; n + 4 <= nc; n += 4) {
+        Real v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = PACK ? g[(size_t)(n + u) * N] : s[(size_t)(n + u) * nz];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (PACK) s[(size_t)(n + u) * nz] = v[u];
+          else g[(size_t)(n + u) * N] = v[u];
+        }
+      }
+      for (; n < nc; ++n) {
+        if (PACK) s[(size_t)n * nz] = g[(size_t)n * N];
+        else g[(size_t)n * N] = s[(size_t)n * nz];
+      }
     }
     var0 += nc;
   }
@@ -118,7 +139,7 @@ extern "C" int pb_halo_pack(const pb_pack_t *pack, const pb_cfg_t *cfg, const do
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (nseg <= 0) return PB_OK;
-  halo_buffer_kernel<true><<<nseg, 256, 0, (cudaStream_t)stream>>>(*pack, *cfg, halo_fields(*pack, *cfg, const_cast<double *>(cons)), plan, buf);
+  halo_buffer_kernel<true><<<dim3(nseg, 8), 256, 0, (cudaStream_t)stream>>>(*pack, *cfg, halo_fields(*pack, *cfg, const_cast<double *>(cons)), plan, buf);
   return check_launch("halo_pack");
 }
 
@@ -127,6 +148,6 @@ extern "C" int pb_halo_unpack(const pb_pack_t *pack, const pb_cfg_t *cfg, double
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (nseg <= 0) return PB_OK;
-  halo_buffer_kernel<false><<<nseg, 256, 0, (cudaStream_t)stream>>>(*pack, *cfg, halo_fields(*pack, *cfg, cons), plan, const_cast<double *>(buf));
+  halo_buffer_kernel<false><<<dim3(nseg, 8), 256, 0, (cudaStream_t)stream>>>(*pack, *cfg, halo_fields(*pack, *cfg, cons), plan, const_cast<double *>(buf));
   return check_launch("halo_unpack");
 }
