@@ -51,6 +51,29 @@ LIVE = {
 }
 
 
+# long runs to the deck's own tlim (one wave period, set by the pgen): stages dumped every `every` cycles
+# and for the last cycle; name -> (binary, deck, overrides, every, geometry kind)
+LONG = {
+    # 2-D MHD fast mode, linear + hll (deck defaults), 4 blocks of 16^2: 123 cycles
+    "linmodes2d_long": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast"]
+                        + B3(32, 32, 1, 16, 16, 1), 40, 0),
+    # 3-D, weno5 + llf, 8 blocks of 8^3
+    "linmodes3d_long": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast", "fluid/recon=weno5",
+                                                     "fluid/riemann=llf"] + B3(16, 16, 16, 8, 8, 8), 30, 0),
+}
+
+
+def run_ref_long(case, outdir):
+    binary, deck, ov, every, _ = case
+    env = dict(os.environ, REF_DUMP_DIR=outdir, OMP_NUM_THREADS="1", REF_DUMP_EVERY=str(every))
+    exe = os.path.join(HERE, "_ref", "ref_dump_" + binary)
+    deckf = os.path.join(HERE, "_ref", "decks", deck + ".pin")
+    with open(os.path.join(outdir, "log.txt"), "w") as log:
+        subprocess.check_call([exe, "-i", deckf] + ov, cwd=outdir, env=env, stdout=log, stderr=subprocess.STDOUT)
+    tags = sorted(f[:-5] for f in os.listdir(outdir) if f.endswith(".json") and f != "init.json")
+    return ["init"] + tags
+
+
 def run_ref(case, outdir, qlqr=False):
     binary, deck, ov, nlim, _ = case
     env = dict(os.environ, REF_DUMP_DIR=outdir, OMP_NUM_THREADS="1")
@@ -67,13 +90,28 @@ def run_ref(case, outdir, qlqr=False):
 def main():
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         tmp = tempfile.mkdtemp(prefix="gold_" + name)
         tags = run_ref(case, tmp)
         out = os.path.join(gold, name + ".npz")
         with open(os.path.join(HERE, "_ref", "decks", case[1] + ".pin")) as f:
             blocks = deckmod.parse_deck(f.read(), case[2])
         refdump.pack_golden(tmp, tags, out, extra_meta={"deck_blocks": blocks, "deck": case[1], "overrides": case[2], "nlim": case[3],
+                                                         "geometry": case[4], "binary": case[0]})
+        shutil.rmtree(tmp)
+        print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
+    for name, case in LONG.items():
+        if only and name not in only:
+            continue
+        tmp = tempfile.mkdtemp(prefix="gold_" + name)
+        tags = run_ref_long(case, tmp)
+        out = os.path.join(gold, name + ".npz")
+        with open(os.path.join(HERE, "_ref", "decks", case[1] + ".pin")) as f:
+            blocks = deckmod.parse_deck(f.read(), case[2])
+        refdump.pack_golden(tmp, tags, out, extra_meta={"deck_blocks": blocks, "deck": case[1], "overrides": case[2], "every": case[3],
                                                          "geometry": case[4], "binary": case[0]})
         shutil.rmtree(tmp)
         print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))

@@ -12,6 +12,7 @@
 //
 // usage: ref_dump -i deck.pin [block/key=value ...]   with env REF_DUMP_DIR=<dir>
 //        REF_DUMP_QLQR=1 additionally dumps ql/qr.
+//        REF_DUMP_EVERY=N dumps only the stages of cycles 0, N, 2N, ... and of the last cycle (long runs).
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -151,6 +152,7 @@ struct Dumper {
 };
 
 Dumper g_dumper;
+int g_every = 1;
 
 class DumpDriver : public phoebus::PhoebusDriver {
  public:
@@ -171,10 +173,13 @@ class DumpDriver : public phoebus::PhoebusDriver {
     if (tm.ncycle == 0) {
       g_dumper.Dump(pmesh, "init", 0, 0, tm.time, tm.dt, 0.0, "base", "base", true);
     }
+    const bool last_cycle = (tm.time + dt_trial >= tm.tlim) || (tm.nlim >= 0 && tm.ncycle + 1 >= tm.nlim);
+    const bool dump_cycle = g_every <= 1 || tm.ncycle % g_every == 0 || last_cycle;
     for (int stage = 1; stage <= integrator->nstages; stage++) {
       TaskCollection tc = RungeKuttaStage(stage);
       status = tc.Execute();
       if (status != TaskListStatus::complete) break;
+      if (!dump_cycle) continue;
       char tag[64];
       std::snprintf(tag, sizeof(tag), "c%04ds%d", tm.ncycle, stage);
       g_dumper.Dump(pmesh, tag, tm.ncycle, stage, tm.time, tm.dt,
@@ -195,6 +200,7 @@ int main(int argc, char *argv[]) {
   const char *d = std::getenv("REF_DUMP_DIR");
   g_dumper.dir = d ? d : ".";
   g_dumper.with_qlqr = std::getenv("REF_DUMP_QLQR") != nullptr;
+  if (const char *e = std::getenv("REF_DUMP_EVERY")) g_every = std::atoi(e);
 
   parthenon::ParthenonManager pman;
   auto manager_status = pman.ParthenonInitEnv(argc, argv);
