@@ -198,6 +198,9 @@ int pb_halo_unpack(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, con
 /* Physical boundary ghost fill + Boundaries::ConvertBoundaryConditions,
  * ref: src/phoebus_boundaries/phoebus_boundaries.cpp:44-448 */
 int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream);
+/* ref: TaskStatus fluid::CalculateDivB(MeshBlockData<Real>*), src/fluid/fluid.cpp:843-897 (diagnostic run with the
+ * last stage of a cycle, ref: src/phoebus_driver.cpp:724-726). divb: device [b][cells], interior zones written. */
+int pb_calculate_divb(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *divb, void *stream);
 /* ref: fluid::EstimateTimestepBlock, src/fluid/fluid.cpp:899-944, min over the pack, without
  * the cfl factor. dt_out: device double, combined with atomic min (caller initialises). */
 int pb_estimate_dt(const pb_pack_t *pack, const pb_cfg_t *cfg, int has_face_speeds, double *dt_out,

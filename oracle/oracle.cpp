@@ -991,6 +991,37 @@ void orc_flux_divergence(const orc_cfg *c, const double *flux, double *dudt) {
         }
 }
 
+// fluid.cpp:843-897 (CalculateDivB): the sums are evaluated left to right as written there
+void orc_divb(const orc_cfg *c, const double *cons, double *divb) {
+  Lay L(c);
+  if (!c->mhd || L.ndim < 2) return;
+  const long N = L.ncell;
+  const Real *b0 = cons + (size_t)5 * N, *b1 = cons + (size_t)6 * N, *b2 = cons + (size_t)7 * N;
+  const long sj = L.ni, sk = (long)L.ni * L.nj;
+  for (int k = L.ks; k <= L.ke; ++k)
+    for (int j = L.js; j <= L.je; ++j)
+      for (int i = L.is; i <= L.ie; ++i) {
+        const long o = L.idx(k, j, i);
+        if (L.ndim == 2) {
+          divb[o] = 0.5 * (b0[o] + b0[o - sj] - b0[o - 1] - b0[o - sj - 1]) / c->dx[0] +
+                    0.5 * (b1[o] + b1[o - 1] - b1[o - sj] - b1[o - sj - 1]) / c->dx[1];
+        } else {
+          divb[o] = 0.25 *
+                        (b0[o] + b0[o - sj] + b0[o - sk] + b0[o - sk - sj] - b0[o - 1] - b0[o - sj - 1] - b0[o - sk - 1] -
+                         b0[o - sk - sj - 1]) /
+                        c->dx[0] +
+                    0.25 *
+                        (b1[o] + b1[o - 1] + b1[o - sk] + b1[o - sk - 1] - b1[o - sj] - b1[o - sj - 1] - b1[o - sk - sj] -
+                         b1[o - sk - sj - 1]) /
+                        c->dx[1] +
+                    0.25 *
+                        (b2[o] + b2[o - 1] + b2[o - sj] + b2[o - sj - 1] - b2[o - sk] - b2[o - sk - 1] - b2[o - sk - sj] -
+                         b2[o - sk - sj - 1]) /
+                        c->dx[2];
+        }
+      }
+}
+
 // fluid.cpp:566-657
 void orc_source_terms(const orc_cfg *c, const double *geom, const double *prim, double *gsrc) {
   Lay L(c);

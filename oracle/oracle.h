@@ -71,6 +71,8 @@ void orc_fix_fluxes(const orc_cfg *c, double *flux);
 /* parthenon::Update::FluxDivergence (update.cpp:63-85): dudt interior only */
 void orc_flux_divergence(const orc_cfg *c, const double *flux, double *dudt);
 /* fluid::CalculateFluidSourceTerms (fluid.cpp:566-657): gsrc[4][cells] = S1,S2,S3,tau */
+/* fluid::CalculateDivB, fluid.cpp:843-897: corner-centred div B of the conserved field, interior zones */
+void orc_divb(const orc_cfg *c, const double *cons, double *divb);
 void orc_source_terms(const orc_cfg *c, const double *geom, const double *prim, double *gsrc);
 /* SumData + AverageIndependentData + UpdateIndependentData (update.hpp:71-136) over entire
  * arrays: dudt[1..4] += gsrc; u0 = beta*u0 + (1-beta)*ubase (in place); uout = u0 + bdt*dudt */

@@ -110,7 +110,7 @@ struct Dumper {
     const std::vector<std::string> onecopy = {
         "p.density",   "p.velocity", "p.energy",          "p.bfield",
         "pressure",    "temperature", "gamma1",           "c2p_mu",
-        "fail",        "cell_signal_speed", "face_signal_speed", "emf"};
+        "fail",        "cell_signal_speed", "face_signal_speed", "emf", "divb"};
     const std::vector<std::string> cons = {"c.density", "c.momentum", "c.energy",
                                            "c.bfield"};
     const std::vector<std::string> geom = {

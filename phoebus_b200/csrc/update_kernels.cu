@@ -439,6 +439,49 @@ extern "C" int pb_source_terms(const pb_pack_t *pack, const pb_cfg_t *cfg, doubl
   return check_launch("source_kernel");
 }
 
+// ref: fluid::CalculateDivB, src/fluid/fluid.cpp:843-897 — corner-centred div B of the conserved field on
+// interior zones; sums left to right as the reference writes them
+template <int NDIM> __global__ void divb_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *cons, Real *divb) {
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (!interior_zone(L, pack.nblocks, 0, 0, 0, b, k, j, i)) return;
+  const int N = L.ncell, o = L.idx(k, j, i);
+  const int sj = L.ni, sk = L.ni * L.nj;
+  const pb_block_t &blk = pack.blocks[b];
+  const Real *b0 = cons + ((size_t)b * 8 + CB) * N, *b1 = b0 + N, *b2 = b1 + N;
+  Real v;
+  if (NDIM == 2) {
+    v = 0.5 * (b0[o] + b0[o - sj] - b0[o - 1] - b0[o - sj - 1]) / blk.dx[0] +
+        0.5 * (b1[o] + b1[o - 1] - b1[o - sj] - b1[o - sj - 1]) / blk.dx[1];
+  } else {
+    v = 0.25 *
+            (b0[o] + b0[o - sj] + b0[o - sk] + b0[o - sk - sj] - b0[o - 1] - b0[o - sj - 1] - b0[o - sk - 1] -
+             b0[o - sk - sj - 1]) /
+            blk.dx[0] +
+        0.25 *
+            (b1[o] + b1[o - 1] + b1[o - sk] + b1[o - sk - 1] - b1[o - sj] - b1[o - sj - 1] - b1[o - sk - sj] -
+             b1[o - sk - sj - 1]) /
+            blk.dx[1] +
+        0.25 *
+            (b2[o] + b2[o - 1] + b2[o - sj] + b2[o - sj - 1] - b2[o - sk] - b2[o - sk - 1] - b2[o - sk - sj] -
+             b2[o - sk - sj - 1]) /
+            blk.dx[2];
+  }
+  divb[(size_t)b * N + o] = v;
+}
+
+extern "C" int pb_calculate_divb(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *divb, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cons || !divb) return set_error(PB_EINVAL, "pb_calculate_divb: NULL argument");
+  if (!cfg->mhd || cfg->ndim < 2) return PB_OK; // ref: fluid.cpp:846, and no 1-D branch there
+  const int T = 256;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->ndim == 2) divb_kernel<2><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, cons, divb);
+  else divb_kernel<3><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, cons, divb);
+  return check_launch("divb_kernel");
+}
+
 extern "C" int pb_weighted_sum(const double *x, const double *y, double w1, double w2, double *z, long long n,
                                void *stream) {
   if (n <= 0) return PB_OK;

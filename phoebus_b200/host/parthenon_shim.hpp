@@ -178,6 +178,7 @@ class Mesh {
   void Upload(const std::string &name, const double *host);
   void Download(const std::string &name, double *host) const;
   void Synchronize() const;
+  double *DivB() const { return field_.at("divb"); } // diagnostic field of fluid::CalculateDivB
   void InvalidateZoneFlags() { flags_valid = false; }
   bool flags_valid = false;
   unsigned long long *counters = nullptr; // device [3]: floors, ceilings, in-kernel c2p failures

@@ -515,6 +515,7 @@ void Mesh::Allocate() {
   field("flux", ndim * ncons);
   field("emf", 3);
   field("gsrc", 4);
+  field("divb", 1);
   pb_block_t *blocks_dev = (pb_block_t *)dev(sizeof(pb_block_t) * nblocks);
   CheckCuda(cudaMemcpy(blocks_dev, blocks_host.data(), sizeof(pb_block_t) * nblocks, cudaMemcpyHostToDevice), "blocks H2D");
   double *geom_dev = (double *)dev(geom_host_.size() * 8);
@@ -745,6 +746,14 @@ template TaskStatus ConservedToPrimitiveRegion<MeshBlockData<Real>>(MeshBlockDat
 template TaskStatus ConservedToPrimitiveRobust<MeshData<Real>>(MeshData<Real> *, const IndexRange &, const IndexRange &, const IndexRange &);
 template TaskStatus ConservedToPrimitiveRobust<MeshBlockData<Real>>(MeshBlockData<Real> *, const IndexRange &, const IndexRange &, const IndexRange &);
 
+static TaskStatus DivBImpl(parthenon::PackView *rc) {
+  if (!FluidActive(rc) || !Pkg(rc, "fluid").Get<bool>("mhd")) return TaskStatus::complete;
+  Mesh *pm = rc->GetMeshPointer();
+  CheckPb(pb_calculate_divb(&rc->pack, Cfg(rc), rc->cons, pm->DivB() + (long long)rc->first * pm->cells, S(rc)), "pb_calculate_divb");
+  return TaskStatus::complete;
+}
+TaskStatus CalculateDivB(MeshBlockData<Real> *rc) { return DivBImpl(rc); }
+TaskStatus CalculateDivB(MeshData<Real> *rc) { return DivBImpl(rc); }
 Real EstimateTimestepBlock(MeshBlockData<Real> *rc) { return DtImpl(rc); }
 Real EstimateTimestepMesh(MeshData<Real> *rc) { return DtImpl(rc); }
 } // namespace fluid
@@ -914,6 +923,7 @@ TaskStatus PhoebusDriver::RungeKuttaStage(int stage) {
     FillDerived(rc.get());
     fixup::ConservedToPrimitiveFixup(rc.get());
     fixup::ApplyFloors(rc.get());
+    if (stage == (int)beta.size()) fluid::CalculateDivB(rc.get()); // ref: phoebus_driver.cpp:719-726
   }
   return TaskStatus::complete;
 }

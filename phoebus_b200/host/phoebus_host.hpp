@@ -42,6 +42,8 @@ TaskStatus ConservedToPrimitiveRobust(T *rc, const IndexRange &ib, const IndexRa
 TaskStatus CalculateFluidSourceTerms(MeshData<Real> *rc, MeshData<Real> *rc_src);
 TaskStatus CalculateFluxes(MeshBlockData<Real> *rc);
 TaskStatus FluxCT(MeshBlockData<Real> *rc);
+TaskStatus CalculateDivB(MeshBlockData<Real> *rc);
+TaskStatus CalculateDivB(MeshData<Real> *rc);
 Real EstimateTimestepBlock(MeshBlockData<Real> *rc);
 // whole-partition overloads (one launch for every block of the GPU instead of one per block)
 TaskStatus CalculateFluxes(MeshData<Real> *rc);

@@ -34,6 +34,7 @@ TASKS = [
     "parthenon::TaskStatus fluid::ConservedToPrimitiveRegion<parthenon::MeshBlockData<double> >(",
     "parthenon::TaskStatus fluid::ConservedToPrimitiveRobust<parthenon::MeshData<double> >(",
     "fluid::EstimateTimestepBlock(parthenon::MeshBlockData<double>*)",
+    "fluid::CalculateDivB(parthenon::MeshBlockData<double>*)",
     "fixup::Initialize(parthenon::ParameterInput*)",
     "fixup::FixFluxes(parthenon::MeshBlockData<double>*)",
     "parthenon::TaskStatus fixup::ApplyFloors<parthenon::MeshData<double> >(parthenon::MeshData<double>*)",
