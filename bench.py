@@ -25,10 +25,10 @@ WEAK_MESH = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512
 # contract-minimum words per zone-stage, 3-D MHD (Nc=8, Nr=10, g=1.953)
 A_TASK_BYTES_PER_ZONE_CYCLE = 2368.0
 G1_WORDS_PER_ZONE_STAGE = 37.0  # CalculateFluxes: R 10 prims, W 3x8 fluxes, W 3 face speeds
-# from the committed ncu captures of this same command (profiles/r01_ncu_recon_riemann.md): dram bytes per launch at
+# from the committed ncu captures of this same command (profiles/r01_ncu_full_bench_256cube.md): dram bytes per launch at
 # 256^3 zones per GPU, and the FP64 pipe utilisation (sm__inst_executed_pipe_fp64 pct of peak sustained active)
-NCU_DRAM_BYTES_PER_LAUNCH = {"recon_kernel": 6.6e9, "flux_kernel": None}
-NCU_FP64_PIPE_PCT = {"recon_kernel": 80.0, "flux_kernel": 50.0}
+NCU_DRAM_BYTES_PER_LAUNCH = {"recon_kernel": 6.08e9, "flux_kernel": None}
+NCU_FP64_PIPE_PCT = {"recon_kernel": 81.9, "flux_kernel": 50.0}
 
 
 def deck_text(name="torus3d"):
@@ -238,7 +238,7 @@ def run_ours(args):
                    "parallelism": "meshblock bricks %s" % "x".join(map(str, mesh.rgrid)),
                    "l2": "working set %.1f GB per GPU >> 126 MB L2" % (mesh.bytes_allocated() / 1e9)},
         "roofline": {"bound": "hbm", "kernel": kname, "co_bound": "fp64 pipe (no FMA contraction: bit parity with the reference)",
-                     "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(kname.split("<")[0]), "traffic_source": "profiles/r01_ncu_recon_riemann.md",
+                     "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(kname.split("<")[0]), "traffic_source": "profiles/r01_ncu_full_bench_256cube.md",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(kname.split("<")[0]), "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "step_frac_of_hbm_roofline": value / world * A_TASK_BYTES_PER_ZONE_CYCLE / (peak * 1e9)},

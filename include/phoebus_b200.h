@@ -201,6 +201,13 @@ int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void 
 /* ref: TaskStatus fluid::CalculateDivB(MeshBlockData<Real>*), src/fluid/fluid.cpp:843-897 (diagnostic run with the
  * last stage of a cycle, ref: src/phoebus_driver.cpp:724-726). divb: device [b][cells], interior zones written. */
 int pb_calculate_divb(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *divb, void *stream);
+/* History reductions of the fluid package (the .hst columns, ref: src/fluid/fluid.cpp:325-347,
+ * src/analysis/history.hpp:50-86) over the interior zones of the pack: out_host = {maximum density (p.density),
+ * total baryon number (sum c.density), total conserved energy tau, total X1, X2, X3 momentum}. Plain sums, as the
+ * reference's (its volume weighting never applies). partial_dev: device scratch, 6 doubles per block.
+ * Synchronises the stream (it returns host values, like the reference's reduction). */
+int pb_history_fluid(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *partial_dev,
+                     double out_host[6], void *stream);
 /* ref: fluid::EstimateTimestepBlock, src/fluid/fluid.cpp:899-944, min over the pack, without
  * the cfl factor. dt_out: device double, combined with atomic min (caller initialises). */
 int pb_estimate_dt(const pb_pack_t *pack, const pb_cfg_t *cfg, int has_face_speeds, double *dt_out,

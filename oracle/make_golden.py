@@ -74,6 +74,21 @@ def run_ref_long(case, outdir):
     return ["init"] + tags
 
 
+def run_ref_hst(case, out_hst):
+    """the reference's own executable with a history output block: one .hst row per cycle
+    (ref: external/parthenon/src/outputs/history.cpp; columns from src/fluid/fluid.cpp:325-347)"""
+    binary, deck, ov, _, _ = case
+    exe = os.path.join(HERE, "_ref", "phoebus_" + binary)
+    deckf = os.path.join(HERE, "_ref", "decks", deck + ".pin")
+    tmp = tempfile.mkdtemp(prefix="hst_")
+    with open(os.path.join(tmp, "log.txt"), "w") as log:
+        subprocess.check_call([exe, "-i", deckf] + ov + ["parthenon/output0/file_type=hst", "parthenon/output0/dt=1e-12"], cwd=tmp,
+                              env=dict(os.environ, OMP_NUM_THREADS="1"), stdout=log, stderr=subprocess.STDOUT)
+    hst = [f for f in os.listdir(tmp) if f.endswith(".hst")]
+    shutil.copy(os.path.join(tmp, hst[0]), out_hst)
+    shutil.rmtree(tmp)
+
+
 def run_ref(case, outdir, qlqr=False):
     binary, deck, ov, nlim, _ = case
     env = dict(os.environ, REF_DUMP_DIR=outdir, OMP_NUM_THREADS="1")
@@ -115,6 +130,7 @@ def main():
                                                          "geometry": case[4], "binary": case[0]})
         shutil.rmtree(tmp)
         print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
+        run_ref_hst(case, os.path.join(gold, name + ".hst"))
 
 
 if __name__ == "__main__":

@@ -1,5 +1,7 @@
 // FluxCT, FixFluxes, FluxDivergence, CalculateFluidSourceTerms, WeightedSumData and their fusion
 // (divergence + geometric sources + RK update in one pass over the interior zones of a pack).
+#include <vector>
+
 #include "pb_device.cuh"
 #include "pb_host.hpp"
 
@@ -468,6 +470,64 @@ template <int NDIM> __global__ void divb_kernel(const pb_pack_t pack, const pb_c
             blk.dx[2];
   }
   divb[(size_t)b * N + o] = v;
+}
+
+// ---- history reductions of the fluid package (ref: src/fluid/fluid.cpp:325-347, History::ReduceOneVar,
+// src/analysis/history.hpp:50-86): max of p.density, sums of c.density, c.energy, c.momentum[3] over interior zones.
+// The reference's volume weighting compares Reducer_t with Kokkos::Sum<Real, ExecSpace> and therefore never applies
+// (Reducer_t is Kokkos::Sum<Real>): the sums are plain sums, as its .hst files show. One CTA per MeshBlock reduces in a
+// fixed tree order; the caller adds the per-block partials in block order, so the result is run-to-run reproducible.
+__global__ void __launch_bounds__(256) history_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *cons, Real *partial) {
+  const Lay L(cfg);
+  const int b = blockIdx.x, N = L.ncell;
+  const int nxi = L.ie - L.is + 1, nxj = L.je - L.js + 1, nxk = L.ke - L.ks + 1;
+  const int nz = nxi * nxj * nxk;
+  const int ncons = 5 + 3 * cfg.mhd, nprim = 7 + 3 * cfg.mhd;
+  Real acc[6] = {-DBL_MAX, 0.0, 0.0, 0.0, 0.0, 0.0}; // max rho, D, tau, S1, S2, S3
+  for (int z = threadIdx.x; z < nz; z += blockDim.x) {
+    const int i = L.is + z % nxi, j = L.js + (z / nxi) % nxj, k = L.ks + z / (nxi * nxj);
+    const int o = L.idx(k, j, i);
+    const Real *u = cons + (size_t)b * ncons * N + o;
+    acc[0] = dmax(acc[0], pack.prim[(size_t)b * nprim * N + o]);
+    acc[1] += u[(size_t)CRHO * N];
+    acc[2] += u[(size_t)CENG * N];
+    acc[3] += u[(size_t)CMOM * N];
+    acc[4] += u[(size_t)(CMOM + 1) * N];
+    acc[5] += u[(size_t)(CMOM + 2) * N];
+  }
+  __shared__ Real sh[6][256];
+  for (int q = 0; q < 6; ++q) sh[q][threadIdx.x] = acc[q];
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      sh[0][threadIdx.x] = dmax(sh[0][threadIdx.x], sh[0][threadIdx.x + off]);
+      for (int q = 1; q < 6; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) partial[(size_t)b * 6 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+extern "C" int pb_history_fluid(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *partial_dev,
+                                double out_host[6], void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cons || !partial_dev || !out_host) return set_error(PB_EINVAL, "pb_history_fluid: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  history_kernel<<<pack->nblocks, 256, 0, s>>>(*pack, *cfg, cons, partial_dev);
+  rc = check_launch("history_kernel");
+  if (rc) return rc;
+  std::vector<double> h((size_t)pack->nblocks * 6);
+  cudaError_t e = cudaMemcpyAsync(h.data(), partial_dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return set_cuda_error(e, "pb_history_fluid");
+  out_host[0] = -DBL_MAX;
+  for (int q = 1; q < 6; ++q) out_host[q] = 0.0;
+  for (int b = 0; b < pack->nblocks; ++b) {
+    out_host[0] = h[(size_t)b * 6] > out_host[0] ? h[(size_t)b * 6] : out_host[0];
+    for (int q = 1; q < 6; ++q) out_host[q] += h[(size_t)b * 6 + q];
+  }
+  return PB_OK;
 }
 
 extern "C" int pb_calculate_divb(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *divb, void *stream) {

@@ -186,6 +186,28 @@ class FluidDriver:
             self.dist.all_reduce(m.dt_dev, op=self.dist.ReduceOp.MIN)
         return m.p.cfl * float(m.dt_dev.item())
 
+    def history(self, cons=None):
+        """the fluid package's .hst columns (ref: src/fluid/fluid.cpp:325-347): dict of maximum density, total baryon
+        number, total conserved energy tau, total X1/X2/X3 momentum; all-reduced over ranks"""
+        m, L = self.m, self.L
+        pk, cfg = self._pk()
+        cons = m.cons["base"] if cons is None else cons
+        if not hasattr(self, "_hist_partial"):
+            self._hist_partial = self.torch.zeros(6 * m.nblocks, dtype=self.torch.float64, device=m.device)
+        out = (C.c_double * 6)()
+        _lib.check(L.pb_history_fluid(pk, cfg, cons.data_ptr(), self._hist_partial.data_ptr(), out, self._stream()), "pb_history_fluid")
+        self.launches += 1
+        v = list(out)
+        if self.dist is not None:
+            t = self.torch.tensor(v, dtype=self.torch.float64, device=m.device)
+            mx = t[:1].clone()
+            self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX)
+            self.dist.all_reduce(t)
+            v = [float(mx[0])] + [float(x) for x in t[1:]]
+        keys = ("maximum density", "total baryon number", "total conserved energy tau", "total X1 momentum",
+                "total X2 momentum", "total X3 momentum")
+        return dict(zip(keys, v))
+
     def step(self, dt=None):
         """One cycle: all RK stages, then the next dt proposal (2x growth limiter)."""
         if dt is None:

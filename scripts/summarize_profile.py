@@ -11,7 +11,7 @@ import re
 import subprocess
 import sys
 
-OURS = re.compile(r"recon_kernel|riemann_kernel|c2p_fixup_packed_kernel|floors_packed_kernel|arith_selftest_kernel|flux_kernel|c2p_kernel|c2p_fixup_kernel|floors_kernel|flags_scan_kernel|update_\w+_kernel|source_kernel|"
+OURS = re.compile(r"recon_kernel|riemann_kernel|riemann_redo_kernel|c2p_redo_kernel|divb_kernel|history_kernel|c2p_fixup_packed_kernel|floors_packed_kernel|arith_selftest_kernel|flux_kernel|c2p_kernel|c2p_fixup_kernel|floors_kernel|flags_scan_kernel|update_\w+_kernel|source_kernel|"
                   r"divergence_kernel|emf_kernel|ct_flux_kernel|fix_fluxes_kernel|halo_\w+_kernel|bc_kernel|p2c_kernel|dt_kernel|"
                   r"weighted_sum_kernel")
 

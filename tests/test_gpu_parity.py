@@ -399,3 +399,55 @@ def test_divb_matches_reference(name):
             assert np.array_equal(mine[sl], want[sl]), (name, tag, mb["gid"])
             checked += 1
     assert checked > 0
+
+
+def _read_hst(path):
+    rows = {}
+    for line in open(path):
+        if line.startswith("#") or not line.strip():
+            continue
+        v = line.split()
+        rows[int(v[2])] = [float(x) for x in v]
+    return rows
+
+
+@pytest.mark.parametrize("name", ["linmodes2d_long", "linmodes3d_long"])
+def test_history_matches_reference_hst(name):
+    """pb_history_fluid on the dumped states vs the .hst file the reference's own executable wrote for the same run
+    (6 significant digits there) and vs a float64 numpy sum of the same dump (summation order only)"""
+    import os
+    import torch
+    from tests.helpers import GOLDEN
+    g, p, mesh, drv, order = _setup(name)
+    hst = _read_hst(os.path.join(GOLDEN, name + ".hst"))
+    ng = mesh.ng
+    sl = (slice(None), slice(None)) + tuple(slice(ng, -ng) if n > 1 else slice(None) for n in mesh.shape)
+    checked = 0
+    for tag in ["init"] + stage_tags(g):
+        man = g.manifest(tag)
+        if tag != "init" and man["stage"] != 2:
+            continue
+        cycle = 0 if tag == "init" else man["cycle"] + 1
+        cons = mesh.cons["base"]
+        if tag == "init":
+            load_product_state(mesh, g, "init")
+        else:
+            get = getter(g, tag)
+            for mb in man["blocks"]:
+                ref = fd.ref_state(get, mb["gid"], mesh.shape, "base")
+                n = order[mb["gid"]]
+                cons[n].copy_(torch.from_numpy(np.ascontiguousarray(ref["cons"])))
+                mesh.prim[n].copy_(torch.from_numpy(np.ascontiguousarray(ref["prim"]).reshape(tuple(mesh.prim[n].shape))))
+        h = drv.history(cons)
+        c = _np(cons)[sl]
+        want = [float(_np(mesh.prim)[sl][:, 0].max()), c[:, 0].sum(), c[:, 4].sum(), c[:, 1].sum(), c[:, 2].sum(), c[:, 3].sum()]
+        got = list(h.values())
+        assert got[0] == want[0]
+        scale = np.abs(c[:, 1:4]).sum() + 1e-300
+        assert np.allclose(got[1:3], want[1:3], rtol=1e-13, atol=0)
+        assert np.all(np.abs(np.array(got[3:]) - np.array(want[3:])) <= 1e-13 * scale)
+        row = hst[cycle]  # time dt cycle nbtotal baryon tau mom1 mom2 mom3 maxrho
+        for mine, theirs in zip([got[1], got[2], got[3], got[4], got[5], got[0]], row[4:10]):
+            assert abs(mine - theirs) <= 6e-6 * abs(theirs) + 1e-6 * scale * 1e-6, (tag, mine, theirs)
+        checked += 1
+    assert checked >= 4
