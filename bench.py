@@ -363,7 +363,7 @@ def run_oracle_port(nx, block, ncycles, threads):
 def cpu_baseline(args, steps=None):
     threads = os.cpu_count() or 1
     nx, block = (128, 64, 64), 32
-    ncycles = steps or 3
+    ncycles = steps or 24  # ~0.33 s per cycle on 16 cores: a 10-20 s sample after the 2 untimed warm-up cycles
     sample = "3-D FMKS torus %dx%dx%d (%d MeshBlocks of %d^3), %d RK2 cycles after 2 warm-up cycles" % (
         nx[0], nx[1], nx[2], (nx[0] // block) * (nx[1] // block) * (nx[2] // block), block, ncycles)
     if ref_binary() and not args.force_port:
@@ -374,7 +374,7 @@ def cpu_baseline(args, steps=None):
         except Exception as e:  # fall through to the port, but say why
             sample += " [reference binary failed: %s]" % str(e)[:120]
     nx = (64, 64, 32)
-    v = run_oracle_port(nx, block, max(1, ncycles - 1), threads)
+    v = run_oracle_port(nx, block, max(1, min(ncycles, 3)), threads)
     return {"value": v, "unit": "zone-cycles/s", "cores": threads, "kind": "port",
             "sample": "oracle port, synthetic torus %dx%dx%d, 32^3 MeshBlocks spread over host threads" % nx}
 
@@ -384,7 +384,7 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     t0 = time.time()
-    cb = cpu_baseline(args, steps=max(1, min(args.steps, 4)))
+    cb = cpu_baseline(args, steps=max(8, min(8 * args.steps, 48)))  # one 'step' = 8 RK2 cycles of the bounded sample
     nx = (128, 64, 64) if cb["kind"] == "reference" else (64, 64, 32)
     out = {"impl": "reference", "metric": "zone-cycles/s", "value": cb["value"], "unit": "zone-cycles/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
