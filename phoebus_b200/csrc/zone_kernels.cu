@@ -66,8 +66,8 @@ template <bool MHD> struct ZonePtr {
 // ARITH 0: the compiler's divide / sqrt. 1: ArithFast with an inline exact re-solve. 2: ArithFast only; a zone
 // whose operands leave the fast path's exponent range writes NOTHING and reports `rejected` (the caller queues
 // it for c2p_redo_kernel).
-template <bool MHD, int ARITH>
-PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const ZonePtr<MHD> &z, int ndim,
+template <bool MHD, int ARITH, class G>
+PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const G &g, const ZonePtr<MHD> &z, int ndim,
                             Real *U, Real *P, unsigned long long *err_count, bool *rejected = nullptr) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   Real temp, sig[3];
@@ -131,8 +131,8 @@ PB_DEV bool c2p_zone_global(const pb_cfg_t &cfg, const FloorCtx &fc, const Point
 enum { ZF_FAIL = 1, ZF_FLOOR = 2, ZF_STALE = 4 };
 
 // first part of ApplyFloors (ref: src/fixup/fixup.cpp:370-440): decides whether the floors apply.
-template <bool MHD>
-PB_DEV bool floors_decide(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const Real *P, Real &drho,
+template <bool MHD, class G>
+PB_DEV bool floors_decide(const pb_cfg_t &cfg, const FloorCtx &fc, const G &g, const Real *P, Real &drho,
                           Real &du, Real &sie_floor) {
   Real rho_floor = 0.0; // ref passes an uninitialised rho_floor; only ExpX1RhoU reads it
   get_floors(cfg, fc.A, fc.B, fc.x1, fc.x2, fc.x3, rho_floor, sie_floor);
@@ -165,13 +165,13 @@ PB_DEV bool floors_decide(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGe
   return (drho > 0. || du > 0.);
 }
 // ceiling test of ApplyFloors (ref: fixup.cpp:505-507) on the given primitives
-PB_DEV bool ceiling_decide(const pb_cfg_t &cfg, const PointGeom &g, const Real *P, Real &W) {
+template <class G> PB_DEV bool ceiling_decide(const pb_cfg_t &cfg, const G &g, const Real *P, Real &W) {
   const Real vpcon[3] = {P[PVEL], P[PVEL + 1], P[PVEL + 2]};
   W = lorentz_factor(vpcon, g);
   return (W > cfg.gam_max || P[PENG] / P[PRHO] > cfg.sie_max);
 }
 // would ApplyFloors change this zone?
-template <bool MHD> PB_DEV bool floors_needed(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const Real *P) {
+template <bool MHD, class G> PB_DEV bool floors_needed(const pb_cfg_t &cfg, const FloorCtx &fc, const G &g, const Real *P) {
   Real drho, du, sf, W;
   if (floors_decide<MHD>(cfg, fc, g, P, drho, du, sf)) return true;
   return ceiling_decide(cfg, g, P, W);
@@ -345,6 +345,9 @@ struct ZoneCtx { // everything a zone task needs, built from the thread's (b,k,j
 // ref: src/fluid/fluid.cpp:477-517. With zflags != NULL the kernel also records, per zone, whether
 // the c2p failed and whether ApplyFloors will have to touch the zone (one extra byte written instead
 // of a second full pass over the primitives).
+#ifndef PB_C2P_MINB
+#define PB_C2P_MINB 5 // 96 registers, 20 warps/SM: measured 11.65 ms vs 11.81 (4 CTAs) and 12.4 (6 CTAs) per cycle
+#endif
 template <bool MHD, int ARITH>
 PB_DEV bool c2p_thread(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, const Lay &L, int b, int k, int j, int i,
                        unsigned long long *err_count, unsigned char *zflags) {
@@ -352,7 +355,7 @@ PB_DEV bool c2p_thread(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, c
   const int o = L.idx(k, j, i);
   const pb_block_t &blk = pack.blocks[b];
   const GeomTab gt(cfg, pack.geom, blk.geom_slot);
-  PointGeom g;
+  PointGeom g; // (a shared-memory metric, SmemGeom, was measured: same spills, no gain)
   g.load(gt, 0, gt.cell(k, j, i));
   const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
   const ZonePtr<MHD> z(pack, cons, L, b, o);
@@ -378,7 +381,7 @@ PB_DEV bool c2p_thread(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, c
 }
 
 template <bool MHD, int ARITH>
-__global__ void __launch_bounds__(128, 4) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+__global__ void __launch_bounds__(128, PB_C2P_MINB) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
                                                      unsigned long long *err_count, unsigned char *zflags, const RedoQueue rq) {
   const Lay L(cfg);
   int b, k, j, i;
