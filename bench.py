@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WEAK_MESH = {1: (256, 256, 256), 2: (512, 256, 256), 4: (512, 512, 256), 8: (512, 512, 512)}
+STRONG_MESH = (256, 128, 128)  # inputs/torus.pin in 3-D: 128 MeshBlocks of 32^3
 # contract-minimum words per zone-stage, 3-D MHD (Nc=8, Nr=10, g=1.953)
 A_TASK_BYTES_PER_ZONE_CYCLE = 2368.0
 G1_WORDS_PER_ZONE_STAGE = 37.0  # CalculateFluxes: R 10 prims, W 3x8 fluxes, W 3 face speeds
@@ -80,7 +81,7 @@ def build_mesh(args, rank, world, device):
     from phoebus_b200.mesh import MeshPack
     from phoebus_b200.params import FluidParams, ParameterInput
     from phoebus_b200.pgen import torus_problem_modifier
-    nx = tuple(args.mesh) if args.mesh else WEAK_MESH[world]
+    nx = tuple(args.mesh) if args.mesh else (STRONG_MESH if args.strong else WEAK_MESH[world])
     ov = ["parthenon/mesh/nx%d=%d" % (d + 1, nx[d]) for d in range(3)]
     ov += ["parthenon/meshblock/nx%d=%d" % (d + 1, args.block) for d in range(3)]
     pin = ParameterInput(deck_text(), ov)
@@ -230,9 +231,10 @@ def run_ours(args):
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     out = {
         "metric": "zone-cycles/s", "value": value, "unit": "zone-cycles/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3-D FMKS torus GRMHD, weak scaling (BASELINE.json configs[4])", "mesh": list(nx),
+        "config": {"workload": "3-D FMKS torus GRMHD, strong scaling, fixed 256x128x128 mesh (BASELINE.json configs[3])" if args.strong
+                   else "3-D FMKS torus GRMHD, weak scaling (BASELINE.json configs[4])", "mesh": list(nx),
                    "meshblock": [args.block] * 3, "zones_per_gpu": zones_rank, "blocks_per_gpu": mesh.nblocks,
                    "recon": fp.recon, "riemann": fp.riemann, "integrator": "rk2", "geometry": "fmks a=0.9375 (host-tabulated, axisymmetric)",
                    "parallelism": "meshblock bricks %s" % "x".join(map(str, mesh.rgrid)),
@@ -405,6 +407,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh", type=int, nargs=3, default=None, help="override the mesh size (zones)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the fixed 256x128x128 torus of inputs/torus.pin (BASELINE.json configs[3]) on N GPUs")
     ap.add_argument("--block", type=int, default=32)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
