@@ -150,22 +150,35 @@ template <bool MHD> __global__ void fix_fluxes_kernel(const pb_pack_t pack, cons
 
 // ------------------------------------------------------------------ divergence / sources
 // ref: external/parthenon/src/interface/update.hpp:43-58 (FluxDivHelper)
-template <int NCn> PB_DEV void flux_div(const Lay &L, const pb_block_t &blk, const Real *fb, int o, Real *du) {
+template <int NCn, int NDIM> PB_DEV void flux_div_nd(const Lay &L, const pb_block_t &blk, const Real *fb, int o, Real *du) {
   // uniform_cartesian.hpp:30-40: face areas and the cell volume are products of dx
   const Real area[3] = {blk.dx[1] * blk.dx[2], blk.dx[0] * blk.dx[2], blk.dx[0] * blk.dx[1]};
   const Real vol = blk.dx[0] * blk.dx[1] * blk.dx[2];
   const int st[3] = {1, L.ni, L.ni * L.nj};
   const int N = L.ncell;
+  // NDIM is a template parameter so that the 2 * NDIM loads of a component are issued together
 #pragma unroll
   for (int l = 0; l < NCn; ++l) {
-    Real acc = 0;
-    for (int d = 0; d < L.ndim; ++d) {
+    Real lo[NDIM], hi[NDIM];
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
       const Real *f = fb + ((size_t)d * NCn + l) * N + o;
-      const Real t = (area[d] * __ldg(f + st[d]) - area[d] * __ldg(f));
+      lo[d] = __ldg(f);
+      hi[d] = __ldg(f + st[d]);
+    }
+    Real acc = 0;
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) {
+      const Real t = (area[d] * hi[d] - area[d] * lo[d]);
       acc = (d == 0) ? t : acc + t;
     }
     du[l] = -acc / vol;
   }
+}
+template <int NCn> PB_DEV void flux_div(const Lay &L, const pb_block_t &blk, const Real *fb, int o, Real *du) {
+  if (L.ndim == 3) flux_div_nd<NCn, 3>(L, blk, fb, o, du);
+  else if (L.ndim == 2) flux_div_nd<NCn, 2>(L, blk, fb, o, du);
+  else flux_div_nd<NCn, 1>(L, blk, fb, o, du);
 }
 
 // ref: src/fluid/fluid.cpp:593-654 with src/fluid/tmunu.hpp:63-131 and
