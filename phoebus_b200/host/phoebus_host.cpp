@@ -878,6 +878,7 @@ PhoebusDriver::PhoebusDriver(ParameterInput *pin, Mesh *pm, bool fused) : pmesh(
   for (size_t i = 1; i < beta.size(); ++i) stage_name.push_back("1");
   stage_name.push_back("base");
   dt_init_fact_ = pin->GetOrAddReal("parthenon/time", "dt_init_fact", 1.0);
+  tlim_ = pin->GetOrAddReal("parthenon/time", "tlim", DBL_MAX);
 }
 
 TaskStatus PhoebusDriver::RungeKuttaStage(int stage) {
@@ -955,6 +956,7 @@ TaskStatus PhoebusDriver::Step() {
   ncycle += 1;
   time += step_dt;
   dt = std::min(2.0 * step_dt, EstimateTimestep()); // ref: parthenon driver.cpp:216-240
+  if (time < tlim_ && (tlim_ - time) < dt) dt = tlim_ - time; // ref: parthenon driver.cpp:236-239
   return TaskStatus::complete;
 }
 

@@ -131,6 +131,7 @@ class PhoebusDriver {
   bool fused_;
   bool first_step_ = true;
   Real dt_init_fact_ = 1.0;
+  Real tlim_ = 0.0;
 };
 
 // packages on the path, in the reference's order (ref: src/phoebus_package.cpp / main.cpp ProcessPackages)

@@ -157,3 +157,38 @@ def test_host_driver_matches_reference_dumps(name, mode, tmp_path):
             for k in ("prim", "temp", "c2p_mu", "fail", "csig"):
                 assert np.array_equal(out[k][n].reshape(ref[k].shape), ref[k], equal_nan=True), (name, mode, tag, k)
             assert np.array_equal(out[man["sc1"]][n], ref["cons"], equal_nan=True), (name, mode, tag, "cons")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fused", "tasks"])
+def test_host_driver_long_run_with_its_own_dt_control(mode, tmp_path):
+    """phoebus_host_stage evolve: PhoebusDriver::Step (EstimateTimestep, 2x limiter, tlim clip) for one full wave
+    period from the reference's init dump must land on the reference's final dump bit for bit"""
+    import torch
+    name = "linmodes2d_long"
+    g, fp, deck = _case_deck(name, tmp_path)
+    mesh, _ = product_mesh(g, device=torch.device("cuda:0"))
+    order = load_product_state(mesh, g, "init")
+    fields = [getattr(mesh, k) for k in STATE_FIELDS] + [mesh.cons["base"], mesh.cons["1"]]
+    sin, sout = os.path.join(str(tmp_path), "in.bin"), os.path.join(str(tmp_path), "out.bin")
+    with open(sin, "wb") as f:
+        for t in fields:
+            f.write(t.cpu().numpy().tobytes())
+    tags = stage_tags(g)
+    last = g.manifest(tags[-1])
+    ncycles = last["cycle"] + 1
+    tlim = last["time"] + last["dt"]
+    r = subprocess.run([EXE, "evolve", deck, sin, sout, mode, str(ncycles), repr(float(g.manifest("init")["dt"])),
+                        "parthenon/time/dt_init_fact=1.0", "parthenon/time/tlim=%r" % float(tlim)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    raw = np.fromfile(sout, dtype=np.float64)
+    off, out = 0, {}
+    for k, t in zip(STATE_FIELDS + ("base", "1"), fields):
+        out[k] = raw[off:off + t.numel()].reshape(tuple(t.shape))
+        off += t.numel()
+    for mb in last["blocks"]:
+        n = order[mb["gid"]]
+        ref = fd.ref_state(getter(g, tags[-1]), mb["gid"], mesh.shape, last["sc1"])
+        for k in ("prim", "temp", "c2p_mu", "fail", "csig"):
+            assert np.array_equal(out[k][n].reshape(ref[k].shape), ref[k], equal_nan=True), (mode, k)
+        assert np.array_equal(out[last["sc1"]][n], ref["cons"], equal_nan=True), (mode, "cons")
