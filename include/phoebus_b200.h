@@ -108,6 +108,9 @@ typedef struct pb_pack {
   int n_bc_blocks;
   double *gsrc;             /* [b][4][cells] the "geometric source terms" container (ref: phoebus_driver.cpp:289-299);
                              * when present the sequencer runs the sources as their own launch */
+  const int *inner_blocks;  /* device [n_inner_blocks]: the blocks NOT in bc_blocks (no mesh boundary on any face);
+                             * optional, used by pb_rk_stage_post_early to start con2prim under an inter-GPU transfer */
+  int n_inner_blocks;
   double *recon_lr;         /* [2][b][nprim][cells] left / right face states of ONE direction at a time (the
                              * reference's ql / qr fields, ref: src/fluid/fluid.cpp:288-299). When present,
                              * pb_calculate_fluxes runs reconstruction and Riemann solve as two launches per
@@ -225,6 +228,13 @@ int pb_rk_stage_pre(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc0, dou
                     double beta, double dt, unsigned long long *counters, void *stream);
 int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1,
                      unsigned long long *counters, void *stream);
+/* The second half in two parts, to hide an inter-GPU halo transfer under interior work: _post_early (con2prim on the
+ * interior zones of pack->inner_blocks) may be issued once the same-GPU halo copy has been launched and before the
+ * remote ghosts have arrived; _post2(early_done = 1) then runs the BCs, con2prim on everything else, fixup and floors.
+ * _post2(early_done = 0) == pb_rk_stage_post. Results are bit-identical either way. */
+int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, void *stream);
+int pb_rk_stage_post2(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, unsigned long long *counters,
+                      int early_done, void *stream);
 
 /* Optional per-task device timing of pb_rk_stage*: CUDA events on the launching stream around each
  * task group. pb_profile_read synchronises the recorded events, returns the accumulated milliseconds

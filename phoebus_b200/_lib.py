@@ -46,7 +46,7 @@ class PbPack(C.Structure):
                 ("prim", C.c_void_p), ("temp", C.c_void_p), ("c2p_mu", C.c_void_p), ("fail", C.c_void_p),
                 ("csig", C.c_void_p), ("fsig", C.c_void_p), ("flux", C.c_void_p), ("emf", C.c_void_p),
                 ("zflags", C.c_void_p), ("bc_blocks", C.c_void_p), ("n_bc_blocks", C.c_int), ("gsrc", C.c_void_p),
-                ("recon_lr", C.c_void_p)]
+                ("inner_blocks", C.c_void_p), ("n_inner_blocks", C.c_int), ("recon_lr", C.c_void_p)]
 
 
 # every symbol include/phoebus_b200.h declares: name -> (restype, argtypes)
@@ -92,6 +92,8 @@ SYMBOLS = {
     "pb_rk_stage": (C.c_int, [_PACK, _CFG, _P, _P, _P, C.c_double, C.c_double, _P, _P]),
     "pb_rk_stage_pre": (C.c_int, [_PACK, _CFG, _P, _P, _P, C.c_double, C.c_double, _P, _P]),
     "pb_rk_stage_post": (C.c_int, [_PACK, _CFG, _P, _P, _P]),
+    "pb_rk_stage_post_early": (C.c_int, [_PACK, _CFG, _P, _P]),
+    "pb_rk_stage_post2": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P]),
 }
 
 _lib = None

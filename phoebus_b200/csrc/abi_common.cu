@@ -202,6 +202,8 @@ extern "C" int pb_profile_read(double *ms, int *calls) {
 namespace pb {
 int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2], const int jb[2], const int kb[2],
                unsigned char *zflags, cudaStream_t s);
+int launch_c2p_list(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, int which,
+                    unsigned char *zflags, cudaStream_t s);
 int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int mode, unsigned char *zflags, cudaStream_t s);
 int launch_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, unsigned long long *counters, int mode,
                   unsigned char *zflags, const double *lazy_u0, const double *lazy_ubase, double beta, cudaStream_t s);
@@ -251,10 +253,26 @@ extern "C" int pb_rk_stage_pre(const pb_pack_t *pack, const pb_cfg_t *cfg, doubl
   return PB_OK;
 }
 
-extern "C" int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, unsigned long long *counters,
-                                void *stream) {
+// Region 9 in two parts, for callers that run an inter-GPU halo exchange: pb_rk_stage_post_early may be issued
+// while the transfer is in flight (after the same-GPU halo copy): it solves con2prim on the INTERIOR zones of the
+// MeshBlocks that touch no mesh boundary (pack->inner_blocks) — zones no ghost fill reads or writes. Blocks on a mesh
+// boundary must wait: with bc_vars = primitive the boundary fill copies the previous stage's primitives of their
+// interior. pb_rk_stage_post2(early_done = 1) then does the rest: BCs, con2prim on the ghost shells of the inner
+// blocks and on the entire boundary blocks, fixup, floors. Zones are independent, so the bits do not change.
+extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!pack->inner_blocks || pack->n_inner_blocks <= 0) return PB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope p(PB_TASK_C2P, s);
+  return launch_c2p_list(pack, cfg, sc1, pack->inner_blocks, pack->n_inner_blocks, 0, pack->zflags, s);
+}
+
+extern "C" int pb_rk_stage_post2(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, unsigned long long *counters,
+                                 int early_done, void *stream) {
   int rc;
   cudaStream_t s = (cudaStream_t)stream;
+  const bool split = early_done && pack->inner_blocks && pack->n_inner_blocks > 0;
   // region 9: BCs -> c2p over the entire block -> fixup -> floors
   {
     ProfScope p(PB_TASK_BCS, s);
@@ -262,24 +280,31 @@ extern "C" int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, doub
   }
   const Lay L(*cfg);
   const int ib[2] = {0, L.ni - 1}, jb[2] = {0, L.nj - 1}, kb[2] = {0, L.nk - 1};
-  if (pack->zflags) {
-    {
-      ProfScope p(PB_TASK_C2P, s);
+  {
+    ProfScope p(PB_TASK_C2P, s);
+    if (split) {
+      if ((rc = launch_c2p_list(pack, cfg, sc1, pack->inner_blocks, pack->n_inner_blocks, 1, pack->zflags, s))) return rc;
+      if ((rc = launch_c2p_list(pack, cfg, sc1, pack->bc_blocks, pack->n_bc_blocks, 2, pack->zflags, s))) return rc;
+    } else if (pack->zflags) {
       if ((rc = launch_c2p(pack, cfg, sc1, ib, jb, kb, pack->zflags, s))) return rc;
+    } else {
+      if ((rc = pb_cons_to_prim(pack, cfg, sc1, ib, jb, kb, stream))) return rc;
     }
-    ProfScope p(PB_TASK_FIXUP_FLOORS, s);
+  }
+  ProfScope p(PB_TASK_FIXUP_FLOORS, s);
+  if (pack->zflags) {
     if ((rc = launch_fixup(pack, cfg, sc1, 1, pack->zflags, s))) return rc;
     if ((rc = launch_floors(pack, cfg, sc1, counters, 1, pack->zflags, nullptr, nullptr, 1.0, s))) return rc;
   } else {
-    {
-      ProfScope p(PB_TASK_C2P, s);
-      if ((rc = pb_cons_to_prim(pack, cfg, sc1, ib, jb, kb, stream))) return rc;
-    }
-    ProfScope p(PB_TASK_FIXUP_FLOORS, s);
     if ((rc = pb_c2p_fixup(pack, cfg, sc1, stream))) return rc;
     if ((rc = pb_apply_floors(pack, cfg, sc1, counters, stream))) return rc;
   }
   return PB_OK;
+}
+
+extern "C" int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, unsigned long long *counters,
+                                void *stream) {
+  return pb_rk_stage_post2(pack, cfg, sc1, counters, 0, stream);
 }
 
 extern "C" int pb_rk_stage(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc0, double *base, double *sc1,

@@ -380,30 +380,56 @@ PB_DEV bool c2p_thread(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, c
   return false;
 }
 
+// Which zones a c2p launch covers: a box of every block (the task as the reference runs it), or — for the stage
+// sequencer that hides the inter-GPU halo transfer under interior work — a list of blocks combined with either a
+// box or the ghost shell. Queue entries are block * ncell + cell so that the redo kernel needs no enumeration.
+struct C2PWork {
+  Region reg;        // box (used unless shell)
+  const int *blocks; // block list or NULL (= all blocks of the pack)
+  int nlist;         // blocks covered
+  int shell;         // 1: ghost shell instead of the box
+};
+PB_DEV bool c2p_zone_of_thread(const C2PWork &w, const Lay &L, int &b, int &k, int &j, int &i) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w.shell) {
+    const Shell sh(L);
+    if (t >= (long long)sh.n * w.nlist) return false;
+    const int q = (int)(t / sh.n);
+    b = w.blocks ? w.blocks[q] : q;
+    sh.cell(L, (int)(t - (long long)q * sh.n), k, j, i);
+    return true;
+  }
+  const long long nreg = w.reg.n();
+  if (t >= nreg * w.nlist) return false;
+  const int q = (int)(t / nreg);
+  b = w.blocks ? w.blocks[q] : q;
+  int rem = (int)(t - (long long)q * nreg);
+  i = w.reg.i0 + rem % w.reg.ni();
+  rem /= w.reg.ni();
+  j = w.reg.j0 + rem % w.reg.nj();
+  k = w.reg.k0 + rem / w.reg.nj();
+  return true;
+}
 template <bool MHD, int ARITH>
-__global__ void __launch_bounds__(128, PB_C2P_MINB) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
-                                                     unsigned long long *err_count, unsigned char *zflags, const RedoQueue rq) {
+__global__ void __launch_bounds__(128, PB_C2P_MINB) c2p_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const C2PWork work,
+                                                               unsigned long long *err_count, unsigned char *zflags, const RedoQueue rq) {
   const Lay L(cfg);
   int b, k, j, i;
-  if (!zone_of_thread(reg, pack.nblocks, b, k, j, i)) return;
+  if (!c2p_zone_of_thread(work, L, b, k, j, i)) return;
   if (c2p_thread<MHD, ARITH>(pack, cfg, cons, L, b, k, j, i, err_count, zflags))
-    rq.list[atomicAdd(rq.count, 1u)] = (unsigned)((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    rq.list[atomicAdd(rq.count, 1u)] = (unsigned)((long long)b * L.ncell + L.idx(k, j, i));
 }
 // zones the fast arithmetic rejected, solved with the compiler's divide / sqrt (see RedoQueue, pb_host.hpp)
 template <bool MHD>
-__global__ void __launch_bounds__(128, 4) c2p_redo_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+__global__ void __launch_bounds__(128, 4) c2p_redo_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons,
                                                           unsigned long long *err_count, unsigned char *zflags, const RedoQueue rq) {
   const Lay L(cfg);
   const unsigned n = *rq.count;
   if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(rq.total, (unsigned long long)n);
-  const long long nreg = reg.n();
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const long long t = rq.list[e];
-    const int b = (int)(t / nreg);
-    int rem = (int)(t % nreg);
-    const int i = reg.i0 + rem % reg.ni();
-    rem /= reg.ni();
-    const int j = reg.j0 + rem % reg.nj(), k = reg.k0 + rem / reg.nj();
+    const unsigned t = rq.list[e];
+    const int b = (int)(t / (unsigned)L.ncell), o = (int)(t % (unsigned)L.ncell);
+    const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
     c2p_thread<MHD, 0>(pack, cfg, cons, L, b, k, j, i, err_count, zflags);
   }
 }
@@ -793,24 +819,22 @@ using namespace pb;
 
 namespace pb {
 // sequencer-internal launchers (abi_common.cu)
-int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2], const int jb[2], const int kb[2],
-               unsigned char *zflags, cudaStream_t s) {
-  const Region reg{ib[0], ib[1], jb[0], jb[1], kb[0], kb[1]};
-  if (reg.n() <= 0) return PB_OK;
+static int launch_c2p_work(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const C2PWork &work, long long nthr,
+                           unsigned char *zflags, cudaStream_t s) {
+  if (nthr <= 0) return PB_OK;
   const int T = zone_threads();
-  const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
-  // PB_C2P_ARITH: queue (default) = ArithFast, rejected zones re-solved by c2p_redo_kernel; exact = the
-  // compiler's divide / sqrt everywhere; inline = ArithFast with the exact re-solve inside the kernel
+  const unsigned grid = grid_for(nthr, T);
+  // option c2p_arith / PB_C2P_ARITH: queue (default) = ArithFast, rejected zones re-solved by c2p_redo_kernel; exact =
+  // the compiler's divide / sqrt everywhere; inline = ArithFast with the exact re-solve inside the kernel
   const int mode = c2p_arith_mode();
   RedoQueue rq{nullptr, nullptr, nullptr};
   if (mode == 2) {
-    const long long nthr = reg.n() * pack->nblocks;
-    if (nthr >= (1ll << 32)) return set_error(PB_EINVAL, "pack too large for the 32-bit redo queue");
+    if ((long long)pack->nblocks * Lay(*cfg).ncell >= (1ll << 32)) return set_error(PB_EINVAL, "pack too large for the 32-bit redo queue");
     int rc = redo_queue((size_t)nthr, rq);
     if (rc) return rc;
     cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
   }
-#define PB_C2P(M, A) c2p_kernel<M, A><<<grid, T, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags, rq)
+#define PB_C2P(M, A) c2p_kernel<M, A><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, err_counter(), zflags, rq)
   if (cfg->mhd) {
     if (mode == 0) PB_C2P(true, 0); else if (mode == 1) PB_C2P(true, 1); else PB_C2P(true, 2);
   } else {
@@ -818,10 +842,28 @@ int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const i
   }
 #undef PB_C2P
   if (mode == 2) {
-    if (cfg->mhd) c2p_redo_kernel<true><<<148 * 4, 128, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags, rq);
-    else c2p_redo_kernel<false><<<148 * 4, 128, 0, s>>>(*pack, *cfg, cons, reg, err_counter(), zflags, rq);
+    if (cfg->mhd) c2p_redo_kernel<true><<<148 * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq);
+    else c2p_redo_kernel<false><<<148 * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq);
   }
   return check_launch("c2p_kernel");
+}
+int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int ib[2], const int jb[2], const int kb[2],
+               unsigned char *zflags, cudaStream_t s) {
+  const Region reg{ib[0], ib[1], jb[0], jb[1], kb[0], kb[1]};
+  if (reg.n() <= 0) return PB_OK;
+  const C2PWork work{reg, nullptr, pack->nblocks, 0};
+  return launch_c2p_work(pack, cfg, cons, work, reg.n() * pack->nblocks, zflags, s);
+}
+// c2p on a list of blocks: which = 0 interior zones, 1 ghost shell, 2 entire block
+int launch_c2p_list(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, int which,
+                    unsigned char *zflags, cudaStream_t s) {
+  if (nlist <= 0) return PB_OK;
+  const Lay L(*cfg);
+  const Shell sh(L);
+  const Region reg = which == 0 ? interior(L) : entire(L);
+  const C2PWork work{reg, blocks, nlist, which == 1 ? 1 : 0};
+  const long long nthr = (which == 1 ? (long long)sh.n : reg.n()) * nlist;
+  return launch_c2p_work(pack, cfg, cons, work, nthr, zflags, s);
 }
 int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int mode, unsigned char *zflags, cudaStream_t s) {
   if (!cfg->enable_c2p_fixup) return PB_OK; // ref: fixup_c2p.cpp:60-62

@@ -26,6 +26,7 @@ class FluidDriver:
         self.time = 0.0
         self.launches = 0
         self.timers = None  # dict -> per-task CUDA-event timing (bench.py)
+        self.force_split = False  # single GPU: sequence the stage as the multi-GPU path does (pre / halo + early c2p / post2)
         if self.dist is not None:
             self._setup_halo_buffers()
 
@@ -72,13 +73,17 @@ class FluidDriver:
         self.rplan = t.from_numpy(rp if len(rp) else np.zeros((1, 10), dtype=np.int32)).to(m.device)
 
     # ------------------------------------------------------------------ tasks
-    def exchange(self, cons):
-        """region 8: SendBoundBufs / ReceiveBoundBufs / SetBounds"""
+    def exchange(self, cons, under_transfer=None):
+        """region 8: SendBoundBufs / ReceiveBoundBufs / SetBounds. `under_transfer`, if given, is called after the
+        same-GPU ghost copy has been launched and before the remote ghosts are waited for (work to hide the
+        NVLink transfer under)."""
         m, L = self.m, self.L
         pk, cfg = self._pk()
         s = self._stream()
         if self.dist is None:
             _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
+            if under_transfer is not None:
+                under_transfer()
             return
         dist = self.dist
         _lib.check(L.pb_halo_pack(pk, cfg, cons.data_ptr(), self.splan.data_ptr(), self.nsend, self.sbuf.data_ptr(), s), "pb_halo_pack")
@@ -89,8 +94,10 @@ class FluidDriver:
             if h["rbuf"].numel():
                 ops.append(dist.P2POp(dist.irecv, h["rbuf"], h["peer"]))
         reqs = dist.batch_isend_irecv(ops) if ops else []
-        # same-GPU neighbours while the NVLink transfers are in flight
+        # same-GPU neighbours, then interior work, while the NVLink transfers are in flight
         _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
+        if under_transfer is not None:
+            under_transfer()
         for r in reqs:
             r.wait()
         _lib.check(L.pb_halo_unpack(pk, cfg, cons.data_ptr(), self.rplan.data_ptr(), self.nrecv, self.rbuf.data_ptr(), s), "pb_halo_unpack")
@@ -113,21 +120,23 @@ class FluidDriver:
         base = m.cons["base"]
         cnt = C.c_void_p(m.counters.data_ptr())
         self.ensure_flags()
-        if self.dist is None:
+        if self.dist is None and not self.force_split:
             _lib.check(L.pb_rk_stage(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s), "pb_rk_stage")
         else:
             _lib.check(L.pb_rk_stage_pre(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s),
                        "pb_rk_stage_pre")
+            # con2prim on the interior of the MeshBlocks away from the mesh boundary runs under the transfer
+            early = lambda: _lib.check(L.pb_rk_stage_post_early(pk, cfg, sc1.data_ptr(), s), "pb_rk_stage_post_early")
             if self.timers is not None:
                 t = self.torch
                 e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
                 e0.record()
-                self.exchange(sc1)
+                self.exchange(sc1, early)
                 e1.record()
-                self.timers.setdefault("halo", []).append((e0, e1))
+                self.timers.setdefault("halo+early_c2p", []).append((e0, e1))
             else:
-                self.exchange(sc1)
-            _lib.check(L.pb_rk_stage_post(pk, cfg, sc1.data_ptr(), cnt, s), "pb_rk_stage_post")
+                self.exchange(sc1, early)
+            _lib.check(L.pb_rk_stage_post2(pk, cfg, sc1.data_ptr(), cnt, 1, s), "pb_rk_stage_post2")
         self.launches += self.LAUNCHES_PER_STAGE
 
     # kernels launched per stage by pb_rk_stage: flux x ndim, emf + ct, fix, [source,] update
@@ -154,6 +163,7 @@ class FluidDriver:
             n += 2
         if self.dist is not None:
             n += 2  # one pack and one unpack launch for all peers
+            n += 2 * (2 if self.L.pb_get_option(b"c2p_arith") == 2 else 1)  # c2p in three launches instead of one
         return n
 
     def enable_profile(self, on=True):

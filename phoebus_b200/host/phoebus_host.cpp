@@ -528,6 +528,13 @@ void Mesh::Allocate() {
     for (int f = 0; f < 2 * ndim; ++f) any = any || blocks_host[n].bc[f] != PB_BC_BLOCK;
     if (any) bcb.push_back(n);
   }
+  std::vector<int> inner;
+  for (int n = 0, q = 0; n < nblocks; ++n) {
+    if (q < (int)bcb.size() && bcb[q] == n) ++q;
+    else inner.push_back(n);
+  }
+  int *inner_dev = (int *)dev(sizeof(int) * std::max<size_t>(1, inner.size()));
+  if (!inner.empty()) CheckCuda(cudaMemcpy(inner_dev, inner.data(), sizeof(int) * inner.size(), cudaMemcpyHostToDevice), "inner list H2D");
   int *bcb_dev = (int *)dev(sizeof(int) * std::max<size_t>(1, bcb.size()));
   if (!bcb.empty()) CheckCuda(cudaMemcpy(bcb_dev, bcb.data(), sizeof(int) * bcb.size(), cudaMemcpyHostToDevice), "bc list H2D");
   counters = (unsigned long long *)dev(3 * sizeof(unsigned long long));
@@ -547,6 +554,8 @@ void Mesh::Allocate() {
   pack_.zflags = (unsigned char *)dev((size_t)nblocks * cells);
   pack_.bc_blocks = bcb_dev;
   pack_.n_bc_blocks = (int)bcb.size();
+  pack_.inner_blocks = inner_dev;
+  pack_.n_inner_blocks = (int)inner.size();
   pack_.gsrc = field_["gsrc"];
   pack_.recon_lr = (double *)dev((size_t)2 * nblocks * nprim * cells * 8); // ql / qr of one direction
   AddContainer("base");
@@ -611,6 +620,8 @@ std::shared_ptr<MeshBlockData<Real>> Mesh::GetBlockData(int b, const std::string
   p.recon_lr = nullptr; // per-block calls use the fused flux kernel
   p.bc_blocks = nullptr; // "every block of this pack"
   p.n_bc_blocks = 0;
+  p.inner_blocks = nullptr;
+  p.n_inner_blocks = 0;
   rc->pack = p;
   rc->cons = cons_[stage] + o * (stage == "geometric source terms" ? 4 : ncons);
   return rc;

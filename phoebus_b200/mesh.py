@@ -272,6 +272,9 @@ class MeshPack:
         bcb = [n for n in range(self.nblocks) if any(self.blocks_host[n].bc[f] != 0 for f in range(2 * self.ndim))]
         self.bc_blocks = t.tensor(bcb if bcb else [0], dtype=t.int32, device=self.device)
         self.n_bc_blocks = len(bcb)
+        inner = [n for n in range(self.nblocks) if n not in set(bcb)]
+        self.inner_blocks = t.tensor(inner if inner else [0], dtype=t.int32, device=self.device)
+        self.n_inner_blocks = len(inner)
         pk = PbPack()
         pk.nblocks = self.nblocks
         pk.blocks = self.blocks_dev.data_ptr()
@@ -284,6 +287,8 @@ class MeshPack:
         pk.recon_lr = self.recon_lr.data_ptr() if self.recon_lr is not None else None
         pk.bc_blocks = self.bc_blocks.data_ptr()
         pk.n_bc_blocks = self.n_bc_blocks
+        pk.inner_blocks = self.inner_blocks.data_ptr()
+        pk.n_inner_blocks = self.n_inner_blocks
         self.pack = pk
         self.flags_valid = False
 

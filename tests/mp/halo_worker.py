@@ -40,7 +40,9 @@ def gpu_mode(periodic):
     from phoebus_b200.mesh import MeshPack
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    fp = make_params((64, 32, 32), 16, periodic)
+    # 8x4x4 MeshBlocks of 16^3: every rank owns blocks away from the mesh boundary, so the con2prim that runs
+    # under the NCCL transfer (pb_rk_stage_post_early) is exercised
+    fp = make_params((128, 64, 64), 16, periodic)
     part = MeshPack(fp, device=dev, rank=rank, world=world)
     whole = MeshPack(fp, device=dev, rank=0, world=1)
     d_part, d_whole = FluidDriver(part, dist), FluidDriver(whole)

@@ -18,6 +18,9 @@ from oracle import from_dump as fd, pyoracle as po
 from tests.helpers import (CASES, block_lx, getter, load_case, load_product_state, oracle_mesh, product_mesh,
                            stage_tags)
 
+import os
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
 FIELDS = ("prim", "temp", "c2p_mu", "fail", "csig")
@@ -451,3 +454,34 @@ def test_history_matches_reference_hst(name):
             assert abs(mine - theirs) <= 6e-6 * abs(theirs) + 1e-6 * scale * 1e-6, (tag, mine, theirs)
         checked += 1
     assert checked >= 4
+
+
+def test_split_post_phase_matches_single_call_stage():
+    """the multi-GPU sequencing (pre / halo + con2prim on inner blocks under the transfer / BCs + the rest) on one GPU
+    against pb_rk_stage, on a mesh with MeshBlocks away from the boundary: identical bits"""
+    import sys
+    import torch
+    sys.path.insert(0, ROOT_DIR) if ROOT_DIR not in sys.path else None
+    import bench
+    from phoebus_b200.driver import FluidDriver
+
+    class A:
+        mesh, block = (128, 64, 64), 16
+    out = []
+    for split in (False, True):
+        mesh, fp, _ = bench.build_mesh(A, 0, 1, _dev())
+        assert mesh.n_inner_blocks > 0 and mesh.n_bc_blocks > 0
+        drv = FluidDriver(mesh)
+        drv.force_split = split
+        bench.init_state(mesh, drv)
+        dt = 0.05 * drv.estimate_dt()
+        for _ in range(3):
+            drv.step(dt)
+            dt = drv.propose_dt(dt)
+        torch.cuda.synchronize()
+        out.append({k: _np(getattr(mesh, k)).copy() for k in ("prim", "temp", "c2p_mu", "fail", "csig")})
+        out[-1]["cons"] = _np(mesh.cons["base"]).copy()
+        out[-1]["counters"] = _np(mesh.counters).copy()
+        out[-1]["dt"] = np.array([dt])
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k], equal_nan=True), k
