@@ -41,7 +41,7 @@ CASES = {
         "torus/seed=7", "torus/u_jitter=0", "fluid/c2p_floor_scale_fac=0.1",
         "parthenon/time/dt_init_fact=1e-2"], 3, 1),
 }
-# larger live-only cases (tests/test_ref_live.py runs these when oracle/_ref exists)
+# larger cases for ad-hoc runs against oracle/_ref (not part of the committed fixtures)
 LIVE = {
     "linmodes3d": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast", "fluid/recon=weno5"]
                    + B3(16, 16, 16, 8, 8, 8), 3, 0),
