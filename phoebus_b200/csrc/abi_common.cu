@@ -263,6 +263,8 @@ extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (!pack->inner_blocks || pack->n_inner_blocks <= 0) return PB_OK;
+  if (!pack->bc_blocks || pack->n_inner_blocks + pack->n_bc_blocks != pack->nblocks)
+    return set_error(PB_EINVAL, "pb_rk_stage_post_early: inner_blocks and bc_blocks must partition the pack");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope p(PB_TASK_C2P, s);
   return launch_c2p_list(pack, cfg, sc1, pack->inner_blocks, pack->n_inner_blocks, 0, pack->zflags, s);
@@ -272,6 +274,10 @@ extern "C" int pb_rk_stage_post2(const pb_pack_t *pack, const pb_cfg_t *cfg, dou
                                  int early_done, void *stream) {
   int rc;
   cudaStream_t s = (cudaStream_t)stream;
+  // the two lists must partition the pack, otherwise some block would get no con2prim
+  if (early_done && pack->inner_blocks && pack->n_inner_blocks > 0 &&
+      (!pack->bc_blocks || pack->n_inner_blocks + pack->n_bc_blocks != pack->nblocks))
+    return set_error(PB_EINVAL, "pb_rk_stage_post2: inner_blocks and bc_blocks must partition the pack");
   const bool split = early_done && pack->inner_blocks && pack->n_inner_blocks > 0;
   // region 9: BCs -> c2p over the entire block -> fixup -> floors
   {
