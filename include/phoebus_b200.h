@@ -211,6 +211,12 @@ int pb_calculate_divb(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *
  * Synchronises the stream (it returns host values, like the reference's reduction). */
 int pb_history_fluid(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *partial_dev,
                      double out_host[6], void *stream);
+/* Horizon-flux history of a black-hole run (ref: src/analysis/history.cpp:25-222, registered in
+ * src/geometry/geometry.cpp:67-99): out_host = {mdot, jet_energy_flux, jet_momentum_flux, magnetic_Phi} at x1 = xh
+ * (FMKS: xh = log(1 + sqrt(1 - a^2))); jets count zones with magnetisation > sigma_cutoff (fluid/sigma_cutoff).
+ * partial_dev: device scratch, 4 doubles per block. Synchronises the stream. */
+int pb_history_torus(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double xh, double sigma_cutoff,
+                     double *partial_dev, double out_host[4], void *stream);
 /* ref: fluid::EstimateTimestepBlock, src/fluid/fluid.cpp:899-944, min over the pack, without
  * the cfl factor. dt_out: device double, combined with atomic min (caller initialises). */
 int pb_estimate_dt(const pb_pack_t *pack, const pb_cfg_t *cfg, int has_face_speeds, double *dt_out,

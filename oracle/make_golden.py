@@ -74,7 +74,7 @@ def run_ref_long(case, outdir):
     return ["init"] + tags
 
 
-def run_ref_hst(case, out_hst):
+def run_ref_hst(case, out_hst, extra=()):
     """the reference's own executable with a history output block: one .hst row per cycle
     (ref: external/parthenon/src/outputs/history.cpp; columns from src/fluid/fluid.cpp:325-347)"""
     binary, deck, ov, _, _ = case
@@ -82,7 +82,7 @@ def run_ref_hst(case, out_hst):
     deckf = os.path.join(HERE, "_ref", "decks", deck + ".pin")
     tmp = tempfile.mkdtemp(prefix="hst_")
     with open(os.path.join(tmp, "log.txt"), "w") as log:
-        subprocess.check_call([exe, "-i", deckf] + ov + ["parthenon/output0/file_type=hst", "parthenon/output0/dt=1e-12"], cwd=tmp,
+        subprocess.check_call([exe, "-i", deckf] + ov + list(extra) + ["parthenon/output0/file_type=hst", "parthenon/output0/dt=1e-12"], cwd=tmp,
                               env=dict(os.environ, OMP_NUM_THREADS="1"), stdout=log, stderr=subprocess.STDOUT)
     hst = [f for f in os.listdir(tmp) if f.endswith(".hst")]
     shutil.copy(os.path.join(tmp, hst[0]), out_hst)
@@ -118,6 +118,8 @@ def main():
                                                          "geometry": case[4], "binary": case[0]})
         shutil.rmtree(tmp)
         print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
+        if name == "torus2d":  # the horizon-flux history columns (mdot, jet fluxes, Phi) of the same run
+            run_ref_hst(case, os.path.join(gold, name + ".hst"), ["parthenon/time/nlim=%d" % case[3]])
     for name, case in LONG.items():
         if only and name not in only:
             continue

@@ -81,6 +81,7 @@ SYMBOLS = {
     "pb_apply_bcs": (C.c_int, [_PACK, _CFG, _P, _P]),
     "pb_calculate_divb": (C.c_int, [_PACK, _CFG, _P, _P, _P]),
     "pb_history_fluid": (C.c_int, [_PACK, _CFG, _P, _P, _D3, _P]),
+    "pb_history_torus": (C.c_int, [_PACK, _CFG, _P, C.c_double, C.c_double, _P, _D3, _P]),
     "pb_estimate_dt": (C.c_int, [_PACK, _CFG, C.c_int, _P, _P]),
     "pb_profile_enable": (C.c_int, [C.c_int]),
     "pb_profile_read": (C.c_int, [_P, _P]),

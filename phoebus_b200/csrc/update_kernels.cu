@@ -543,6 +543,141 @@ extern "C" int pb_history_fluid(const pb_pack_t *pack, const pb_cfg_t *cfg, cons
   return PB_OK;
 }
 
+// ---- horizon-flux history of the torus (ref: src/analysis/history.cpp:25-222, history_utils.hpp:35-180; registered in
+// src/geometry/geometry.cpp:67-99 when the coordinate system has a horizon parameter "xh"): mdot, jet energy and
+// momentum flux (zones with magnetisation > fluid/sigma_cutoff), magnetic flux Phi. Each is the cell-centred flux of the
+// zone column that contains x1 = xh, linearly interpolated to xh with a centred slope, times dx2 dx3.
+struct HistCell { // what the four flux functions read at (k, j, i)
+  PointGeom g;
+  Real rho, v[3], B[3];
+};
+template <bool MHD> PB_DEV void hist_load(const pb_pack_t &pack, const pb_cfg_t &cfg, const Lay &L, int b, int k, int j, int i, HistCell &c) {
+  constexpr int NP = NC<MHD>::nprim;
+  const GeomTab gt(cfg, pack.geom, pack.blocks[b].geom_slot);
+  c.g.load(gt, 0, gt.cell(k, j, i));
+  const Real *p = pack.prim + (size_t)b * NP * L.ncell + L.idx(k, j, i);
+  c.rho = p[0];
+  for (int a = 0; a < 3; ++a) {
+    c.v[a] = p[(size_t)(PVEL + a) * L.ncell];
+    c.B[a] = MHD ? p[(size_t)(PB_ + a) * L.ncell] : 0.0;
+  }
+}
+PB_DEV Real hist_bsq(const HistCell &c, Real W) { // phoebus::GetMagneticFieldSquared, relativity_utils.hpp:131-141
+  Real Bsq = 0, Bdotv = 0;
+  for (int m = 0; m < 3; ++m)
+    for (int n = 0; n < 3; ++n) {
+      Bdotv += c.g.g4(m + 1, n + 1) * ratio(c.v[m], W) * c.B[n];
+      Bsq += c.g.g4(m + 1, n + 1) * c.B[m] * c.B[n];
+    }
+  return ratio(Bsq, W * W) + Bdotv * Bdotv;
+}
+PB_DEV Real hist_mass_flux(const HistCell &c) { // CalcMassFlux
+  const Real W = lorentz_factor(c.v, c.g);
+  const Real ucon = c.v[0] - c.g.beta[0] * W / c.g.alpha;
+  return -c.g.alpha * c.g.detgam * c.rho * ucon;
+}
+PB_DEV Real hist_sigma(const HistCell &c) { // CalcMagnetization
+  const Real W = lorentz_factor(c.v, c.g);
+  return hist_bsq(c, W) / c.rho;
+}
+PB_DEV void hist_em_fluxes(const HistCell &c, Real &en, Real &mom) { // CalcEMEnergyFlux, CalcEMMomentumFlux
+  const Real W = lorentz_factor(c.v, c.g);
+  Real Bdotv = 0.0, vcov[3] = {0, 0, 0}, Bcov[3] = {0, 0, 0};
+  for (int m = 0; m < 3; ++m)
+    for (int n = 0; n < 3; ++n) {
+      vcov[m] += c.g.g4(m + 1, n + 1) * c.v[n];
+      Bcov[m] += c.g.g4(m + 1, n + 1) * c.B[n];
+      Bdotv += c.g.g4(m + 1, n + 1) * c.B[m] * ratio(c.v[n], W);
+    }
+  const Real lapse = c.g.alpha;
+  const Real b0 = Bdotv * W / lapse;
+  const Real ucov0 = -W * lapse;
+  const Real ucon1 = c.v[0] - c.g.beta[0] * W / lapse;
+  const Real ucov1 = vcov[0];
+  const Real bcon1 = ratio((c.B[0] + lapse * b0 * ucon1), W);
+  const Real bcov1 = ratio((Bcov[0] + lapse * b0 * ucov1), W);
+  const Real bsq = hist_bsq(c, W);
+  const Real T_EM_10 = bsq * ucon1 * ucov0 - bcon1 * b0;
+  const Real T_EM_11 = bsq * ucon1 * ucov1 - bcon1 * bcov1 + 0.5 * bsq;
+  en = +T_EM_10 * lapse * c.g.detgam;
+  mom = -T_EM_11 * lapse * c.g.detgam;
+}
+template <bool MHD>
+__global__ void __launch_bounds__(128) history_torus_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *cons, Real xh,
+                                                            Real sigma_cutoff, Real *partial) {
+  const Lay L(cfg);
+  const int b = blockIdx.x, N = L.ncell;
+  const pb_block_t &blk = pack.blocks[b];
+  const int nxj = L.je - L.js + 1, nxk = L.ke - L.ks + 1;
+  Real acc[4] = {0.0, 0.0, 0.0, 0.0}; // mdot, jet energy flux, jet momentum flux, Phi (before the 0.5)
+  // the interior zone column whose faces bracket xh (at most one per block)
+  int ih = -1;
+  for (int i = L.is; i <= L.ie; ++i)
+    if (Xf(blk, 0, i) <= xh && xh < Xf(blk, 0, i + 1)) ih = i;
+  if (ih >= 0) {
+    const Real dx1 = blk.dx[0], dx2 = blk.dx[1], dx3 = blk.dx[2];
+    for (int z = threadIdx.x; z < nxj * nxk; z += blockDim.x) {
+      const int j = L.js + z % nxj, k = L.ks + z / nxj;
+      HistCell c0, cm, cp;
+      hist_load<MHD>(pack, cfg, L, b, k, j, ih, c0);
+      hist_load<MHD>(pack, cfg, L, b, k, j, ih - 1, cm);
+      hist_load<MHD>(pack, cfg, L, b, k, j, ih + 1, cp);
+      {
+        const Real m = (hist_mass_flux(cp) - hist_mass_flux(cm)) / (2.0 * dx1);
+        acc[0] += (hist_mass_flux(c0) + (xh - Xc(blk, 0, ih)) * m) * dx2 * dx3;
+      }
+      if (MHD) {
+        if (hist_sigma(c0) > sigma_cutoff) {
+          Real e0, p0, em, pm, ep, pp;
+          hist_em_fluxes(c0, e0, p0);
+          hist_em_fluxes(cm, em, pm);
+          hist_em_fluxes(cp, ep, pp);
+          acc[1] += (e0 + (xh - Xc(blk, 0, ih)) * ((ep - em) / (2.0 * dx1))) * dx2 * dx3;
+          acc[2] += (p0 + (xh - Xc(blk, 0, ih)) * ((pp - pm) / (2.0 * dx1))) * dx2 * dx3;
+        }
+        // Phi is evaluated one zone further out (i + 1), ref: history.cpp:208-218
+        const Real *cb = cons + ((size_t)b * 8 + CB) * N;
+        auto phi = [&](int i) {
+          const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+          return fabs(cb[L.idx(k, j, i)]) * gt.at(0, G_ALPHA, gt.cell(k, j, i));
+        };
+        const Real m = (phi(ih + 2) - phi(ih)) / (2.0 * dx1);
+        acc[3] += (phi(ih + 1) + (xh - Xc(blk, 0, ih + 1)) * m) * dx2 * dx3;
+      }
+    }
+  }
+  __shared__ Real sh[4][128];
+  for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] = acc[q];
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off)
+      for (int q = 0; q < 4; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) partial[(size_t)b * 4 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+extern "C" int pb_history_torus(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double xh, double sigma_cutoff,
+                                double *partial_dev, double out_host[4], void *stream) {
+  int rc = check_args(pack, cfg);
+  if (rc) return rc;
+  if (!cons || !partial_dev || !out_host) return set_error(PB_EINVAL, "pb_history_torus: NULL argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cfg->mhd) history_torus_kernel<true><<<pack->nblocks, 128, 0, s>>>(*pack, *cfg, cons, xh, sigma_cutoff, partial_dev);
+  else history_torus_kernel<false><<<pack->nblocks, 128, 0, s>>>(*pack, *cfg, cons, xh, sigma_cutoff, partial_dev);
+  rc = check_launch("history_torus_kernel");
+  if (rc) return rc;
+  std::vector<double> h((size_t)pack->nblocks * 4);
+  cudaError_t e = cudaMemcpyAsync(h.data(), partial_dev, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return set_cuda_error(e, "pb_history_torus");
+  for (int q = 0; q < 4; ++q) out_host[q] = 0.0;
+  for (int b = 0; b < pack->nblocks; ++b)
+    for (int q = 0; q < 4; ++q) out_host[q] += h[(size_t)b * 4 + q];
+  out_host[3] *= 0.5; // 0.5 int detg B^r dx2 dx3
+  return PB_OK;
+}
+
 extern "C" int pb_calculate_divb(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *divb, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;

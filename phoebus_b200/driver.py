@@ -218,6 +218,27 @@ class FluidDriver:
                 "total X2 momentum", "total X3 momentum")
         return dict(zip(keys, v))
 
+    def history_torus(self, cons=None, sigma_cutoff=1.0):
+        """mdot, jet_energy_flux, jet_momentum_flux, magnetic_Phi at the horizon (ref: src/analysis/history.cpp:25-222)"""
+        import math
+        m, L = self.m, self.L
+        pk, cfg = self._pk()
+        cons = m.cons["base"] if cons is None else cons
+        if not hasattr(self, "_hist_partial4"):
+            self._hist_partial4 = self.torch.zeros(4 * m.nblocks, dtype=self.torch.float64, device=m.device)
+        a = m.p.geom_par["a"]
+        xh = math.log(1.0 + math.sqrt(1.0 - a * a))  # ref: src/geometry/fmks.cpp:55-57
+        out = (C.c_double * 4)()
+        _lib.check(L.pb_history_torus(pk, cfg, cons.data_ptr(), xh, sigma_cutoff, self._hist_partial4.data_ptr(), out, self._stream()),
+                   "pb_history_torus")
+        self.launches += 1
+        v = list(out)
+        if self.dist is not None:
+            t = self.torch.tensor(v, dtype=self.torch.float64, device=m.device)
+            self.dist.all_reduce(t)
+            v = [float(x) for x in t]
+        return dict(zip(("mdot", "jet_energy_flux", "jet_momentum_flux", "magnetic_Phi"), v))
+
     def step(self, dt=None):
         """One cycle: all RK stages, then the next dt proposal (2x growth limiter)."""
         if dt is None:
