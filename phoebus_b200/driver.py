@@ -42,32 +42,10 @@ class FluidDriver:
         pack / unpack plan covering every segment: 2 copy launches per exchange instead of 2 per peer."""
         import numpy as np
         t, m = self.torch, self.m
-        plans = sorted(m.halo_plans().items())
-        stot = sum(sn for _, ((_, sn), _) in plans)
-        rtot = sum(rn for _, (_, (_, rn)) in plans)
+        sp, stot, rp, rtot, peers = m.merged_halo_plans()
         self.sbuf = t.empty(max(stot, 1), dtype=t.float64, device=m.device)
         self.rbuf = t.empty(max(rtot, 1), dtype=t.float64, device=m.device)
-
-        def shifted(plan, base):
-            rows = plan.view(np.uint32).astype(np.uint64)
-            off = rows[:, 7] | (rows[:, 8] << np.uint64(32))
-            off += np.uint64(base)
-            out = plan.copy().view(np.uint32)
-            out[:, 7] = (off & np.uint64(0xFFFFFFFF)).astype(np.uint32)
-            out[:, 8] = (off >> np.uint64(32)).astype(np.uint32)
-            return out.view(np.int32)
-
-        self.halo, sall, rall, so, ro = [], [], [], 0, 0
-        for peer, ((splan, sn), (rplan, rn)) in plans:
-            self.halo.append(dict(peer=peer, sbuf=self.sbuf[so:so + sn], rbuf=self.rbuf[ro:ro + rn]))
-            if len(splan):
-                sall.append(shifted(splan, so))
-            if len(rplan):
-                rall.append(shifted(rplan, ro))
-            so += sn
-            ro += rn
-        cat = lambda lst: np.ascontiguousarray(np.concatenate(lst, axis=0)) if lst else np.zeros((0, 10), dtype=np.int32)
-        sp, rp = cat(sall), cat(rall)
+        self.halo = [dict(peer=peer, sbuf=self.sbuf[ss], rbuf=self.rbuf[rs]) for peer, ss, rs in peers]
         self.nsend, self.nrecv = len(sp), len(rp)
         self.splan = t.from_numpy(sp if len(sp) else np.zeros((1, 10), dtype=np.int32)).to(m.device)
         self.rplan = t.from_numpy(rp if len(rp) else np.zeros((1, 10), dtype=np.int32)).to(m.device)

@@ -368,3 +368,28 @@ class MeshPack:
             plans[peer] = out
         self._plans = plans
         return plans
+
+    def merged_halo_plans(self):
+        """All peers in ONE send and ONE receive buffer: (send plan, send words, recv plan, recv words,
+        [(peer, send slice, recv slice)]). Segment offsets of the per-peer plans are shifted by the peer's slice
+        start, so that a single pb_halo_pack / pb_halo_unpack launch serves every peer and NCCL moves the slices."""
+        def shifted(plan, base):
+            rows = plan.view(np.uint32).astype(np.uint64)
+            off = (rows[:, 7] | (rows[:, 8] << np.uint64(32))) + np.uint64(base)
+            out = plan.copy().view(np.uint32)
+            out[:, 7] = (off & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+            out[:, 8] = (off >> np.uint64(32)).astype(np.uint32)
+            return out.view(np.int32)
+
+        sall, rall, peers, so, ro = [], [], [], 0, 0
+        for peer, ((splan, sn), (rplan, rn)) in sorted(self.halo_plans().items()):
+            peers.append((peer, slice(so, so + sn), slice(ro, ro + rn)))
+            if len(splan):
+                sall.append(shifted(splan, so))
+            if len(rplan):
+                rall.append(shifted(rplan, ro))
+            so += sn
+            ro += rn
+        cat = lambda lst: np.ascontiguousarray(np.concatenate(lst, axis=0)) if lst else np.zeros((0, 10), dtype=np.int32)
+        return cat(sall), so, cat(rall), ro, peers
+
