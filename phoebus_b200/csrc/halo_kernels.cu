@@ -61,12 +61,15 @@ __global__ void halo_local_kernel(const pb_pack_t pack, const pb_cfg_t cfg, cons
     const Real *src = hf.ptr[f] + (size_t)nb * nc * N + so;
     Real *dst = hf.ptr[f] + (size_t)b * nc * N + o;
     int n = 0;
-    for (; n + 4 <= nc; n += 4) { // four independent loads in flight per thread (the copy is latency bound otherwise)
-      const Real v0 = src[(size_t)n * N], v1 = src[(size_t)(n + 1) * N], v2 = src[(size_t)(n + 2) * N], v3 = src[(size_t)(n + 3) * N];
-      dst[(size_t)n * N] = v0;
-      dst[(size_t)(n + 1) * N] = v1;
-      dst[(size_t)(n + 2) * N] = v2;
-      dst[(size_t)(n + 3) * N] = v3;
+#ifndef PB_HALO_ILP
+#define PB_HALO_ILP 4
+#endif
+    for (; n + PB_HALO_ILP <= nc; n += PB_HALO_ILP) { // independent loads in flight per thread (the copy is latency bound otherwise)
+      Real v[PB_HALO_ILP];
+#pragma unroll
+      for (int u = 0; u < PB_HALO_ILP; ++u) v[u] = src[(size_t)(n + u) * N];
+#pragma unroll
+      for (int u = 0; u < PB_HALO_ILP; ++u) dst[(size_t)(n + u) * N] = v[u];
     }
     for (; n < nc; ++n) dst[(size_t)n * N] = src[(size_t)n * N];
   }
