@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
   for (int n = 0; n < NP; ++n) {
     const Real *p = v + (size_t)n * L.ncell;
     Real a, c;
-    recon5<RECON>(af, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), a, c);
+    recon5z<RECON>(af, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), a, c);
     l[(size_t)n * L.ncell] = a;
     r[(size_t)n * L.ncell] = c;
   }
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
     for (int n = 0; n < NP; ++n) {
       const Real *p = v + (size_t)n * L.ncell;
       Real a, c;
-      recon5<RECON>(ax, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), a, c);
+      recon5z<RECON>(ax, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), a, c);
       l[(size_t)n * L.ncell] = a;
       r[(size_t)n * L.ncell] = c;
     }
