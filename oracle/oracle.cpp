@@ -991,6 +991,120 @@ void orc_flux_divergence(const orc_cfg *c, const double *flux, double *dudt) {
         }
 }
 
+// ---------------------------------------------------------------- history (.hst columns)
+// fluid.cpp:325-347, analysis/history.hpp:50-86. Reducer_t is Kokkos::Sum<Real> / Kokkos::Max<Real>; the
+// volume_weighting test compares it with Kokkos::Sum<Real, ExecSpace> and is false: plain sums.
+void orc_history_fluid(const orc_cfg *c, const double *prim, const double *cons, double out[6]) {
+  Lay L(c);
+  const long N = L.ncell;
+  out[0] = -DBL_MAX;
+  for (int q = 1; q < 6; ++q) out[q] = 0.0;
+  for (int k = L.ks; k <= L.ke; ++k)
+    for (int j = L.js; j <= L.je; ++j)
+      for (int i = L.is; i <= L.ie; ++i) {
+        const long o = L.idx(k, j, i);
+        out[0] = std::max(out[0], prim[o]);
+        out[1] += cons[o];
+        out[2] += cons[4 * N + o];
+        for (int d = 0; d < 3; ++d) out[3 + d] += cons[(1 + d) * N + o];
+      }
+}
+
+namespace {
+struct HistCell {
+  Real lapse, gdet, shift[3], g4[4][4], gam[3][3], rho, v[3], B[3];
+};
+void hist_load(const orc_cfg *c, const Geom &g, const Lay &L, const double *prim, int k, int j, int i, HistCell &h) {
+  const long N = L.ncell, o = L.idx(k, j, i);
+  h.lapse = g.Lapse(0, k, j, i);
+  h.gdet = g.DetGamma(0, k, j, i);
+  g.Shift(0, k, j, i, h.shift);
+  g.SpacetimeMetric(0, k, j, i, h.g4);
+  g.Metric(0, k, j, i, h.gam);
+  h.rho = prim[o];
+  for (int d = 0; d < 3; ++d) {
+    h.v[d] = prim[(1 + d) * N + o];
+    h.B[d] = c->mhd ? prim[(5 + d) * N + o] : 0.0;
+  }
+}
+// relativity_utils.hpp:131-141
+Real hist_bsq(const HistCell &h, Real W) {
+  Real Bsq = 0, Bdotv = 0;
+  for (int m = 0; m < 3; ++m)
+    for (int n = 0; n < 3; ++n) {
+      Bdotv += h.gam[m][n] * ratio(h.v[m], W) * h.B[n];
+      Bsq += h.gam[m][n] * h.B[m] * h.B[n];
+    }
+  return ratio(Bsq, W * W) + Bdotv * Bdotv;
+}
+// history_utils.hpp:35-56
+Real hist_mass_flux(const HistCell &h) {
+  const Real W = LorentzFactor4(h.v, h.g4);
+  const Real ucon = h.v[0] - h.shift[0] * W / h.lapse;
+  return -h.lapse * h.gdet * h.rho * ucon;
+}
+// history_utils.hpp:58-76
+Real hist_sigma(const HistCell &h) {
+  const Real W = LorentzFactor3(h.v, h.gam);
+  return hist_bsq(h, W) / h.rho;
+}
+// history_utils.hpp:78-160
+void hist_em(const HistCell &h, Real &en, Real &mom) {
+  const Real W = LorentzFactor3(h.v, h.gam);
+  Real Bdotv = 0.0, vcov[3] = {0, 0, 0}, Bcov[3] = {0, 0, 0};
+  for (int m = 0; m < 3; ++m)
+    for (int n = 0; n < 3; ++n) {
+      vcov[m] += h.gam[m][n] * h.v[n];
+      Bcov[m] += h.gam[m][n] * h.B[n];
+      Bdotv += h.gam[m][n] * h.B[m] * ratio(h.v[n], W);
+    }
+  const Real b0 = Bdotv * W / h.lapse;
+  const Real ucov0 = -W * h.lapse;
+  const Real ucon1 = h.v[0] - h.shift[0] * W / h.lapse;
+  const Real ucov1 = vcov[0];
+  const Real bcon1 = ratio((h.B[0] + h.lapse * b0 * ucon1), W);
+  const Real bcov1 = ratio((Bcov[0] + h.lapse * b0 * ucov1), W);
+  const Real bsq = hist_bsq(h, W);
+  en = +(bsq * ucon1 * ucov0 - bcon1 * b0) * h.lapse * h.gdet;
+  mom = -(bsq * ucon1 * ucov1 - bcon1 * bcov1 + 0.5 * bsq) * h.lapse * h.gdet;
+}
+} // namespace
+
+// analysis/history.cpp:25-222: fluxes through x1 = xh, interpolated from the zone column that contains it
+void orc_history_torus(const orc_cfg *c, const double *geom, const double *prim, const double *cons, double xh,
+                       double sigma_cutoff, double out[4]) {
+  Lay L(c);
+  Geom g(c, geom);
+  const long N = L.ncell;
+  for (int q = 0; q < 4; ++q) out[q] = 0.0;
+  const Real dx1 = c->dx[0], dx2 = c->dx[1], dx3 = c->dx[2];
+  for (int k = L.ks; k <= L.ke; ++k)
+    for (int j = L.js; j <= L.je; ++j)
+      for (int i = L.is; i <= L.ie; ++i) {
+        if (!(Xf(c, 0, i) <= xh && xh < Xf(c, 0, i + 1))) continue;
+        HistCell c0, cm, cp;
+        hist_load(c, g, L, prim, k, j, i, c0);
+        hist_load(c, g, L, prim, k, j, i - 1, cm);
+        hist_load(c, g, L, prim, k, j, i + 1, cp);
+        {
+          const Real m = (hist_mass_flux(cp) - hist_mass_flux(cm)) / (2.0 * dx1);
+          out[0] += (hist_mass_flux(c0) + (xh - Xc(c, 0, i)) * m) * dx2 * dx3;
+        }
+        if (!c->mhd) continue;
+        if (hist_sigma(c0) > sigma_cutoff) {
+          Real e0, p0, em, pm, ep, pp;
+          hist_em(c0, e0, p0);
+          hist_em(cm, em, pm);
+          hist_em(cp, ep, pp);
+          out[1] += (e0 + (xh - Xc(c, 0, i)) * ((ep - em) / (2.0 * dx1))) * dx2 * dx3;
+          out[2] += (p0 + (xh - Xc(c, 0, i)) * ((pp - pm) / (2.0 * dx1))) * dx2 * dx3;
+        }
+        auto phi = [&](int ii) { return std::fabs(cons[5 * N + L.idx(k, j, ii)]) * g.Lapse(0, k, j, ii); };
+        const Real m = (phi(i + 2) - phi(i)) / (2.0 * dx1);
+        out[3] += (phi(i + 1) + (xh - Xc(c, 0, i + 1)) * m) * dx2 * dx3;
+      }
+}
+
 // fluid.cpp:843-897 (CalculateDivB): the sums are evaluated left to right as written there
 void orc_divb(const orc_cfg *c, const double *cons, double *divb) {
   Lay L(c);

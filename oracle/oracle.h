@@ -71,6 +71,13 @@ void orc_fix_fluxes(const orc_cfg *c, double *flux);
 /* parthenon::Update::FluxDivergence (update.cpp:63-85): dudt interior only */
 void orc_flux_divergence(const orc_cfg *c, const double *flux, double *dudt);
 /* fluid::CalculateFluidSourceTerms (fluid.cpp:566-657): gsrc[4][cells] = S1,S2,S3,tau */
+/* History reductions (the .hst columns). fluid package, fluid.cpp:325-347 + analysis/history.hpp:50-86 (plain sums:
+ * the volume weighting never applies): out[6] = max p.density, sum c.density, sum c.energy, sum c.momentum[3].
+ * geometry package, analysis/history.cpp:25-222 + history_utils.hpp:35-180: out[4] = mdot, jet energy flux,
+ * jet momentum flux, 2 * magnetic Phi (the caller halves the total) for this block. */
+void orc_history_fluid(const orc_cfg *c, const double *prim, const double *cons, double out[6]);
+void orc_history_torus(const orc_cfg *c, const double *geom, const double *prim, const double *cons, double xh,
+                       double sigma_cutoff, double out[4]);
 /* fluid::CalculateDivB, fluid.cpp:843-897: corner-centred div B of the conserved field, interior zones */
 void orc_divb(const orc_cfg *c, const double *cons, double *divb);
 void orc_source_terms(const orc_cfg *c, const double *geom, const double *prim, double *gsrc);

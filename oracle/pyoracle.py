@@ -101,6 +101,8 @@ def lib():
     L.orc_flux_divergence.argtypes = [cp, dp, dp]
     L.orc_source_terms.argtypes = [cp, dp, dp, dp]
     L.orc_divb.argtypes = [cp, dp, dp]
+    L.orc_history_fluid.argtypes = [cp, dp, dp, dp]
+    L.orc_history_torus.argtypes = [cp, dp, dp, dp, C.c_double, C.c_double, dp]
     L.orc_rk_update.argtypes = [cp, dp, C.c_void_p, dp, dp, C.c_double, C.c_double, dp]
     L.orc_cons_to_prim.argtypes = [cp, dp, dp, dp, dp, dp, dp, dp, ip2, ip2, ip2]
     L.orc_c2p_fixup.argtypes = [cp, dp, dp, dp, dp, dp, dp]

@@ -496,6 +496,7 @@ def test_torus_history_matches_reference_hst():
     from tests.helpers import GOLDEN
     name = "torus2d"
     g, p, mesh, drv, order = _setup(name)
+    om = oracle_mesh(g, p)
     hst = _read_hst(os.path.join(GOLDEN, name + ".hst"))
     checked = 0
     for tag in ["init"] + stage_tags(g):
@@ -525,5 +526,18 @@ def test_torus_history_matches_reference_hst():
         assert ht["jet_energy_flux"] == row[10] == 0.0 and ht["jet_momentum_flux"] == row[11] == 0.0
         # Phi: the field has not reached the horizon, the reference reports 0 or underflow-level leakage
         assert abs(ht["magnetic_Phi"] - row[12]) <= 6e-6 * abs(row[12]) + 1e-100, (tag, ht["magnetic_Phi"], row[12])
+        # and against the oracle's restatement at full precision (only the summation order differs)
+        import math
+        a = mesh.p.geom_par["a"]
+        xh = math.log(1.0 + math.sqrt(1.0 - a * a))
+        tor = np.zeros(4)
+        for mb, ob in zip(man["blocks"], om.blocks):
+            n = order[mb["gid"]]
+            o4 = np.zeros(4)
+            po.lib().orc_history_torus(C.byref(ob.cfg), ob.geom, np.ascontiguousarray(_np(mesh.prim[n])),
+                                       np.ascontiguousarray(_np(cons[n])), xh, 1.0, o4)
+            tor += o4
+        tor[3] *= 0.5
+        assert abs(ht["mdot"] - tor[0]) <= 1e-12 * abs(tor[0]) and abs(ht["magnetic_Phi"] - tor[3]) <= 1e-12 * abs(tor[3]) + 1e-300
         checked += 1
     assert checked == 4
