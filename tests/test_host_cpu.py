@@ -157,3 +157,30 @@ def test_rank_grid_bricks():
     assert sorted(rank_grid(4, [16, 8, 8], 3)) == [1, 2, 2]
     assert rank_grid(2, [8, 4, 4], 3) == [2, 1, 1]
     assert rank_grid(1, [8, 4, 4], 3) == [1, 1, 1]
+
+
+def test_abi_argument_errors_without_a_gpu():
+    """error behaviour of the C ABI that needs no device: bad arguments return PB_EINVAL (-1) with a message,
+    never throw, never touch CUDA; options round-trip; on a box without a GPU a launch reports PB_ECUDA"""
+    from phoebus_b200 import _lib
+    L = _lib.lib()
+    g, p = load_case("torus2d")
+    mesh, fp = product_mesh(g, alloc_fields=False)
+    cfg = mesh.cfg
+    pack = _lib.PbPack()
+    assert L.pb_calculate_fluxes(None, C.byref(cfg), None) == -1 and b"NULL" in L.pb_last_error()
+    assert L.pb_calculate_fluxes(C.byref(pack), C.byref(cfg), None) == -1 and b"no blocks" in L.pb_last_error()
+    pack.nblocks = 1
+    assert L.pb_cons_to_prim(C.byref(pack), C.byref(cfg), None, None, None, None, None) == -1
+    assert b"NULL pack field" in L.pb_last_error()
+    bad = type(cfg).from_buffer_copy(cfg)
+    bad.ndim = 4
+    assert L.pb_flux_ct(C.byref(pack), C.byref(bad), None) == -1 and b"ndim" in L.pb_last_error()
+    assert L.pb_set_option(b"no_such_option", 1) == -1
+    assert L.pb_set_option(b"c2p_arith", 7) == -1
+    old = L.pb_get_option(b"flux_split")
+    assert L.pb_set_option(b"flux_split", 0) == 0 and L.pb_get_option(b"flux_split") == 0
+    assert L.pb_set_option(b"flux_split", old) == 0
+    assert L.pb_nprim(C.byref(cfg)) == 10 and L.pb_ncons(C.byref(cfg)) == 8
+    assert L.pb_cells_per_block(C.byref(cfg)) == mesh.ncell
+    assert L.pb_selftest_arith(0, 1, 8, None, None) == -1
