@@ -541,3 +541,32 @@ def test_torus_history_matches_reference_hst():
         assert abs(ht["mdot"] - tor[0]) <= 1e-12 * abs(tor[0]) and abs(ht["magnetic_Phi"] - tor[3]) <= 1e-12 * abs(tor[3]) + 1e-300
         checked += 1
     assert checked == 4
+
+
+def test_e2e_duplex_pipeline_matches_naive_loop():
+    """bench.py's e2e loop (state in pinned host buffers between cycles; uploads of cycle n+1 overlapped per field with
+    the downloads of cycle n) must leave the same bytes in the host buffers as upload -> cycle -> download -> sync"""
+    import sys
+    import torch
+    sys.path.insert(0, ROOT_DIR) if ROOT_DIR not in sys.path else None
+    import bench
+    from phoebus_b200.driver import FluidDriver
+
+    class A:
+        mesh, block = (64, 64, 64), 32
+    results = []
+    for pipelined in (False, True):
+        mesh, fp, _ = bench.build_mesh(A, 0, 1, _dev())
+        drv = FluidDriver(mesh)
+        bench.init_state(mesh, drv)
+        dt = 0.05 * drv.estimate_dt()
+        dev_t = [mesh.prim, mesh.temp, mesh.c2p_mu, mesh.fail, mesh.cons["base"]]
+        host_t = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in dev_t]
+        for h, d in zip(host_t, dev_t):
+            h.copy_(d)
+        torch.cuda.synchronize()
+        bench.e2e_cycles(torch, drv, host_t, dev_t, 3, dt, pipelined=pipelined)
+        torch.cuda.synchronize()
+        results.append([h.numpy().copy() for h in host_t])
+    for a, b in zip(*results):
+        assert np.array_equal(a, b, equal_nan=True)
