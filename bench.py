@@ -117,6 +117,13 @@ def e2e_cycles(torch, drv, host_t, dev_t, steps, dt, pipelined=True):
     field by events; the cycle itself starts when all of its inputs have arrived. Same bytes, same results as the
     naive upload -> cycle -> download -> synchronize loop (tests/test_gpu_parity.py)."""
     main = torch.cuda.current_stream()
+    if pipelined:  # finer pipeline grain: MeshBlock groups of the big fields, so the uploads trail the downloads closely
+        hs, ds = [], []
+        for h, d in zip(host_t, dev_t):
+            k = 8 if d.numel() > (1 << 20) and d.shape[0] >= 8 else 1
+            hs += list(h.chunk(k, dim=0))
+            ds += list(d.chunk(k, dim=0))
+        host_t, dev_t = hs, ds
     if not pipelined:
         for _ in range(steps):
             for h, d in zip(host_t, dev_t):
