@@ -41,13 +41,44 @@ CASES = {
         "torus/seed=7", "torus/u_jitter=0", "fluid/c2p_floor_scale_fac=0.1",
         "parthenon/time/dt_init_fact=1e-2"], 3, 1),
 }
+# ---- round 2: the benchmarked configuration and the branches no round-1 fixture reached
+TORUS_BASE = ["torus/seed=7", "torus/u_jitter=0", "parthenon/time/dt_init_fact=1e-2"]
+CASES.update({
+    # configs[3]/[4] in small: 3-D FMKS torus, 4 MeshBlocks of 16x8x8, deck defaults (c2p_floor_scale_fac = 1); the harness
+    # perturbs rho, u, v^3 by +-2.5 % with a hash of the global zone index, so the state is genuinely 3-D
+    "torus3d": ("fmks", "torus", B3(32, 16, 8, 16, 8, 8) + TORUS_BASE, 1, 1, {"REF_DUMP_PERTURB": "0.05"}),
+    # ConservedToPrimitiveFixup on real failures: c2p_fail_on_floors marks every zone whose solve touched a floor
+    "torus2d_fail": ("fmks", "torus", B3(32, 16, 1, 16, 8, 1) + TORUS_BASE + ["fluid/c2p_fail_on_floors=true"], 2, 1,
+                     {"REF_DUMP_PERTURB": "0.05"}),
+    # polar X2 boundaries (FixFluxes B2 mirror, sign flips in the ghost fill), primitive and conserved bc_vars
+    "torus2d_polar": ("fmks", "torus", B3(32, 16, 1, 16, 8, 1) + TORUS_BASE + [
+        "parthenon/mesh/ix2_bc=polar", "parthenon/mesh/ox2_bc=polar", "phoebus/ix2_bc=polar", "phoebus/ox2_bc=polar"], 2, 1,
+        {"REF_DUMP_PERTURB": "0.05"}),
+    # (polar requires bc_vars = primitive in the reference, phoebus_boundaries.cpp:167.) gr_outflow with
+    # bc_vars = conserved in curved space: the sqrt(gamma) ratio of the conserved ghost fill is != 1
+    "torus2d_cons": ("fmks", "torus", B3(32, 16, 1, 16, 8, 1) + TORUS_BASE + ["phoebus/mesh/bc_vars=conserved"], 2, 1,
+                     {"REF_DUMP_PERTURB": "0.05"}),
+    # reflecting walls on all six faces (FixFluxes reflect branches, ghost sign flips, edge / corner composition)
+    "reflect3d": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast", "fixup/enable_flux_fixup=true"]
+                  + B3(16, 8, 8, 8, 8, 8) + ["parthenon/mesh/%sx%d_bc=reflect" % (io, d) for d in (1, 2, 3) for io in "io"]
+                  + ["phoebus/%sx%d_bc=reflect" % (io, d) for d in (1, 2, 3) for io in "io"], 2, 0,
+                  {"REF_DUMP_PERTURB": "0.2"}),
+    "reflect2d_prim": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast", "fixup/enable_flux_fixup=true",
+                                                   "phoebus/mesh/bc_vars=primitive"]
+                       + B3(16, 16, 1, 8, 8, 1) + ["parthenon/mesh/%sx%d_bc=reflect" % (io, d) for d in (1, 2) for io in "io"]
+                       + ["phoebus/%sx%d_bc=reflect" % (io, d) for d in (1, 2) for io in "io"], 2, 0,
+                       {"REF_DUMP_PERTURB": "0.2"}),
+})
+# the production block shape: 3-D FMKS torus with 32^3 MeshBlocks (2x2x2 of them), stored as per-array hashes
+# (REF_DUMP_FIELDS=hash); the test rebuilds the initial state with the product's own torus pgen + the same perturbation
+HASHED = {
+    "torus3d_b32": ("fmks", "torus", B3(64, 64, 64, 32, 32, 32) + TORUS_BASE, 2, 1,
+                    {"REF_DUMP_PERTURB": "0.05", "REF_DUMP_FIELDS": "hash"}),
+}
 # larger cases for ad-hoc runs against oracle/_ref (not part of the committed fixtures)
 LIVE = {
     "linmodes3d": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast", "fluid/recon=weno5"]
                    + B3(16, 16, 16, 8, 8, 8), 3, 0),
-    "torus3d": ("fmks", "torus", B3(32, 16, 8, 16, 8, 8) + [
-        "torus/seed=7", "torus/u_jitter=0", "fluid/c2p_floor_scale_fac=0.1",
-        "parthenon/time/dt_init_fact=1e-2"], 12, 1),
 }
 
 
@@ -90,8 +121,9 @@ def run_ref_hst(case, out_hst, extra=()):
 
 
 def run_ref(case, outdir, qlqr=False):
-    binary, deck, ov, nlim, _ = case
+    binary, deck, ov, nlim = case[:4]
     env = dict(os.environ, REF_DUMP_DIR=outdir, OMP_NUM_THREADS="1")
+    env.update(case[5] if len(case) > 5 else {})
     if qlqr:
         env["REF_DUMP_QLQR"] = "1"
     exe = os.path.join(HERE, "_ref", "ref_dump_" + binary)
@@ -115,11 +147,24 @@ def main():
         with open(os.path.join(HERE, "_ref", "decks", case[1] + ".pin")) as f:
             blocks = deckmod.parse_deck(f.read(), case[2])
         refdump.pack_golden(tmp, tags, out, extra_meta={"deck_blocks": blocks, "deck": case[1], "overrides": case[2], "nlim": case[3],
-                                                         "geometry": case[4], "binary": case[0]})
+                                                         "geometry": case[4], "binary": case[0],
+                                                         "env": case[5] if len(case) > 5 else {}})
         shutil.rmtree(tmp)
         print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
         if name == "torus2d":  # the horizon-flux history columns (mdot, jet fluxes, Phi) of the same run
             run_ref_hst(case, os.path.join(gold, name + ".hst"), ["parthenon/time/nlim=%d" % case[3]])
+    for name, case in HASHED.items():
+        if only and name not in only:
+            continue
+        tmp = tempfile.mkdtemp(prefix="gold_" + name)
+        tags = run_ref(case, tmp)
+        out = os.path.join(gold, name + ".json")
+        with open(os.path.join(HERE, "_ref", "decks", case[1] + ".pin")) as f:
+            blocks = deckmod.parse_deck(f.read(), case[2])
+        refdump.pack_hashed(tmp, tags, out, extra_meta={"deck_blocks": blocks, "deck": case[1], "overrides": case[2], "nlim": case[3],
+                                                        "geometry": case[4], "binary": case[0], "env": case[5]})
+        shutil.rmtree(tmp)
+        print(name, "->", out, "%.2f MB" % (os.path.getsize(out) / 1e6))
     for name, case in LONG.items():
         if only and name not in only:
             continue

@@ -239,7 +239,9 @@ class OracleMesh:
         for b in self.blocks:
             c = b.cfg
             out = b.cons[sc1]
-            L.orc_apply_bcs(cp(c), b.geom, out, b.prim, b.temp, b.c2p_mu, b.fail, b.csig)
+            # the reference fills the physical ghosts twice (inside AddBoundaryExchangeTasks and again as set_bc,
+            # phoebus_driver.cpp:646-661; the fill is idempotent) and converts them ONCE (convert_bc): with
+            # bc_vars = conserved the conversion is not idempotent (its c2p advances the ghost zones' c2p_mu history)
             L.orc_apply_bcs(cp(c), b.geom, out, b.prim, b.temp, b.c2p_mu, b.fail, b.csig)
             ib, jb, kb = b.entire()
             L.orc_cons_to_prim(cp(c), b.geom, out, b.prim, b.temp, b.c2p_mu, b.fail, b.csig, ib, jb, kb)

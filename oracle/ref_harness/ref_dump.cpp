@@ -13,8 +13,15 @@
 // usage: ref_dump -i deck.pin [block/key=value ...]   with env REF_DUMP_DIR=<dir>
 //        REF_DUMP_QLQR=1 additionally dumps ql/qr.
 //        REF_DUMP_EVERY=N dumps only the stages of cycles 0, N, 2N, ... and of the last cycle (long runs).
+//        REF_DUMP_PERTURB=amp multiplies p.density, p.energy and p.velocity[2] of every zone (ghosts included) by
+//        1 + amp * (h - 0.5) right after the problem generator and re-runs fluid::PrimitiveToConserved; h is an
+//        integer hash of the zone's GLOBAL index (periodic in x3) in [0, 1), exactly representable, so that a test
+//        can rebuild the same 3-D initial state from an axisymmetric pgen (phoebus_b200/pgen.py: hash_perturbation).
+//        REF_DUMP_FIELDS=hash writes, instead of the raw fields of the stage dumps, one FNV-1a 64-bit hash per array
+//        (large fixtures; the "init" dump keeps one k-plane per array for diagnostics).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -27,6 +34,7 @@
 #include "phoebus_driver.hpp"
 #undef private
 
+#include "fluid/fluid.hpp"
 #include "geometry/geometry.hpp"
 #include "pgen/pgen.hpp"
 #include "phoebus_boundaries/phoebus_boundaries.hpp"
@@ -35,14 +43,30 @@ using namespace parthenon::driver::prelude;
 
 namespace {
 
+// position-weighted sum of the canonicalised bit patterns (−0 -> +0, any NaN -> one pattern), modulo 2^64; the same
+// three lines of numpy reproduce it (oracle/refdump.py: array_hash)
+inline unsigned long long ArrayHash(const Real *p, size_t n) {
+  unsigned long long h = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double y = p[i] + 0.0;
+    unsigned long long b;
+    std::memcpy(&b, &y, 8);
+    if (y != y) b = 0x7ff8000000000000ULL;
+    const unsigned long long w = ((unsigned long long)i * 0x9E3779B97F4A7C15ULL + 0xD1B54A32D192ED03ULL) | 1ULL;
+    h += b * w;
+  }
+  return h;
+}
+
 struct Dumper {
   std::string dir;
   bool with_qlqr = false;
+  bool hash_only = false;
   int ndump = 0;
 
-  static void AppendVar(std::ofstream &bin, std::ostringstream &js, bool &first,
-                        const std::string &container, const std::string &name, int gid,
-                        parthenon::Variable<Real> &v, size_t &offset) {
+  void AppendVar(std::ofstream &bin, std::ostringstream &js, bool &first,
+                 const std::string &container, const std::string &name, int gid,
+                 parthenon::Variable<Real> &v, size_t &offset) {
     if (!v.IsAllocated()) return;
     size_t n = 1;
     int dims[6];
@@ -51,9 +75,16 @@ struct Dumper {
       n *= dims[d - 1];
     }
     auto h = v.data.GetHostMirrorAndCopy();
-    bin.write(reinterpret_cast<const char *>(h.data()), n * sizeof(Real));
     if (!first) js << ",\n";
     first = false;
+    if (hash_only) {
+      js << "  {\"container\":\"" << container << "\",\"name\":\"" << name
+         << "\",\"gid\":" << gid << ",\"dims\":[" << dims[5] << "," << dims[4] << ","
+         << dims[3] << "," << dims[2] << "," << dims[1] << "," << dims[0]
+         << "],\"count\":" << n << ",\"hash\":\"" << std::hex << ArrayHash(h.data(), n) << std::dec << "\"}";
+      return;
+    }
+    bin.write(reinterpret_cast<const char *>(h.data()), n * sizeof(Real));
     js << "  {\"container\":\"" << container << "\",\"name\":\"" << name
        << "\",\"gid\":" << gid << ",\"dims\":[" << dims[5] << "," << dims[4] << ","
        << dims[3] << "," << dims[2] << "," << dims[1] << "," << dims[0]
@@ -154,6 +185,46 @@ struct Dumper {
 Dumper g_dumper;
 int g_every = 1;
 
+// REF_DUMP_PERTURB: see the header comment. Global zone index = (block origin - mesh origin) / dx + local index;
+// x3 wraps (periodic), x1 / x2 ghosts beyond the mesh get indices < 0 or >= nx, shifted by +4096 to stay positive.
+inline double HashUnit(long gi, long gj, long gk, long salt) {
+  unsigned long long x = (unsigned long long)(gi + 4096) * 73856093ULL ^ (unsigned long long)(gj + 4096) * 19349663ULL ^
+                         (unsigned long long)(gk + 4096) * 83492791ULL ^ (unsigned long long)salt * 2654435761ULL;
+  x ^= x >> 15;
+  x *= 0x2c1b3c6dULL;
+  x ^= x >> 12;
+  return (double)(x & 1023ULL) / 1024.0;
+}
+void PerturbState(Mesh *pmesh, double amp) {
+  const int ng = parthenon::Globals::nghost;
+  const long nx3 = pmesh->mesh_size.nx(X3DIR);
+  for (auto &pmb : pmesh->block_list) {
+    auto &rc = pmb->meshblock_data.Get();
+    auto rho = rc->Get("p.density").data;
+    auto eng = rc->Get("p.energy").data;
+    auto vel = rc->Get("p.velocity").data;
+    const auto &c = pmb->coords;
+    auto ib = pmb->cellbounds.GetBoundsI(IndexDomain::entire);
+    auto jb = pmb->cellbounds.GetBoundsJ(IndexDomain::entire);
+    auto kb = pmb->cellbounds.GetBoundsK(IndexDomain::entire);
+    const bool d2 = pmesh->ndim >= 2, d3 = pmesh->ndim >= 3;
+    const long o1 = std::lround((c.Xf<1>(ng) - pmesh->mesh_size.xmin(X1DIR)) / c.Dxc<1>());
+    const long o2 = d2 ? std::lround((c.Xf<2>(ng) - pmesh->mesh_size.xmin(X2DIR)) / c.Dxc<2>()) : 0;
+    const long o3 = d3 ? std::lround((c.Xf<3>(ng) - pmesh->mesh_size.xmin(X3DIR)) / c.Dxc<3>()) : 0;
+    for (int k = kb.s; k <= kb.e; ++k)
+      for (int j = jb.s; j <= jb.e; ++j)
+        for (int i = ib.s; i <= ib.e; ++i) {
+          const long gi = o1 + i - ng, gj = d2 ? o2 + j - ng : 0;
+          long gk = d3 ? o3 + k - ng : 0;
+          if (d3) gk = ((gk % nx3) + nx3) % nx3;
+          rho(k, j, i) *= 1.0 + amp * (HashUnit(gi, gj, gk, 1) - 0.5);
+          eng(k, j, i) *= 1.0 + amp * (HashUnit(gi, gj, gk, 2) - 0.5);
+          vel(2, k, j, i) *= 1.0 + amp * (HashUnit(gi, gj, gk, 3) - 0.5);
+        }
+    fluid::PrimitiveToConserved(rc.get());
+  }
+}
+
 class DumpDriver : public phoebus::PhoebusDriver {
  public:
   using phoebus::PhoebusDriver::PhoebusDriver;
@@ -201,6 +272,7 @@ int main(int argc, char *argv[]) {
   g_dumper.dir = d ? d : ".";
   g_dumper.with_qlqr = std::getenv("REF_DUMP_QLQR") != nullptr;
   if (const char *e = std::getenv("REF_DUMP_EVERY")) g_every = std::atoi(e);
+  if (const char *e = std::getenv("REF_DUMP_FIELDS")) g_dumper.hash_only = std::string(e) == "hash";
 
   parthenon::ParthenonManager pman;
   auto manager_status = pman.ParthenonInitEnv(argc, argv);
@@ -219,6 +291,7 @@ int main(int argc, char *argv[]) {
   phoebus::ProblemModifier(pman.pinput.get());
   Boundaries::ProcessBoundaryConditions(pman);
   pman.ParthenonInitPackagesAndMesh();
+  if (const char *e = std::getenv("REF_DUMP_PERTURB")) PerturbState(pman.pmesh.get(), std::atof(e));
   {
     if (!pman.IsRestart()) {
       phoebus::PostInitializationModifier(pman.pinput.get(), pman.pmesh.get());

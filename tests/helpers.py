@@ -5,7 +5,9 @@ from oracle import deck, from_dump as fd, refdump
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASES = ["shocktube", "linmodes2d", "blast3d", "torus2d"]
+CASES = ["shocktube", "linmodes2d", "blast3d", "torus2d",
+         # round 2: 3-D FMKS (the benchmarked configuration), real c2p failures, polar / reflect / conserved-FMKS boundaries
+         "torus3d", "torus2d_fail", "torus2d_polar", "torus2d_cons", "reflect3d", "reflect2d_prim"]
 
 
 def load_case(name):
