@@ -137,6 +137,28 @@ int pb_build_geometry_host(int kind, const double *par, const pb_cfg_t *cfg, con
 int pb_build_floor_table_host(const pb_cfg_t *cfg, const double xmin[3], const double dx[3],
                               double *out_host);
 
+/* ---- problem generator: Fishbone-Moncrief torus (ref: src/pgen/torus.cpp) ------------------- */
+/* Host table of the torus solution over one MeshBlock column (the solution is axisymmetric; log / exp / pow / sin /
+ * cos evaluated with the host libm in the reference's order, ref: torus.cpp:285-333,745-833).
+ * geom_par as pb_build_geometry_host; torus_par = {rin, rmax, kappa, Gamma, nsub}; geom_tab_host = the geometry table
+ * of the same MeshBlock column (the pgen reads the metric through the cached system's interpolating accessors,
+ * ref: src/geometry/cached_system.hpp:132-236). out_host[5][tk][nj][ni] = rho, u, W v^1, W v^2, W v^3 inside the torus,
+ * 0 outside (before jitter and floors); tk = cfg->gk. PB_EINVAL where the reference aborts ("discr < 0"). */
+int pb_pgen_torus_table_host(const double *geom_par, const double *torus_par, const pb_cfg_t *cfg, const double xmin[3],
+                             const double dx[3], const double *geom_tab_host, double *out_host);
+/* ref: torus.cpp:285-362 — p.density, p.velocity, p.energy (x (1 + u_jitter (rand - 0.5))), atmosphere at the floors,
+ * temperature, pressure, gamma1 on every zone of the pack; p.bfield = 0. table_dev: [geom slot][5][gk][nj][ni]. */
+int pb_pgen_torus_fill(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *table_dev, double u_jitter,
+                       unsigned long long seed, void *stream);
+/* ref: torus.cpp:435-470 — A_phi = max(<rho>_corner - 0.2, 0), p.bfield = curl A / sqrt(gamma) (unnormalised) */
+int pb_pgen_torus_bfield(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stream);
+/* ref: torus.cpp:849-930 (ComputeBetas) over the interior zones of the pack: out_host = {min beta over zones with
+ * rho > rho_min_bnorm, max b^2, max pressure}. partial_dev: 3 doubles per block. Synchronises the stream. */
+int pb_pgen_betas(const pb_pack_t *pack, const pb_cfg_t *cfg, double rho_min_bnorm, double *partial_dev,
+                  double out_host[3], void *stream);
+/* ref: torus.cpp:721-728 — p.bfield *= factor on interior zones */
+int pb_scale_bfield(const pb_pack_t *pack, const pb_cfg_t *cfg, double factor, void *stream);
+
 /* ---- tasks ------------------------------------------------------------------------------ */
 /* ref: TaskStatus fluid::CalculateFluxes(MeshBlockData<Real>*), src/fluid/fluid.cpp:659-773.
  * Fused reconstruction + Riemann solve per direction; writes pack->flux and pack->fsig. */
@@ -201,6 +223,9 @@ int pb_halo_unpack(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, con
 /* Physical boundary ghost fill + Boundaries::ConvertBoundaryConditions,
  * ref: src/phoebus_boundaries/phoebus_boundaries.cpp:44-448 */
 int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream);
+/* The two halves separately: what = 1 ghost fill only (parthenon::ApplyBoundaryConditions as Mesh::Initialize's
+ * CommunicateBoundaries runs it, ref: external/parthenon/src/mesh/mesh.cpp:692-706), 2 conversion only, 3 both. */
+int pb_apply_bcs_ex(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int what, void *stream);
 /* ref: TaskStatus fluid::CalculateDivB(MeshBlockData<Real>*), src/fluid/fluid.cpp:843-897 (diagnostic run with the
  * last stage of a cycle, ref: src/phoebus_driver.cpp:724-726). divb: device [b][cells], interior zones written. */
 int pb_calculate_divb(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, double *divb, void *stream);

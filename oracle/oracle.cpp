@@ -1408,12 +1408,17 @@ void orc_prim_to_cons(const orc_cfg *c, const double *geom, const double *prim, 
 // (external/parthenon/src/mesh/domain.hpp:180-240), followed by ConvertBoundaryConditions.
 void orc_apply_bcs(const orc_cfg *c, const double *geom, double *cons, double *prim, double *temp,
                    double *c2p_mu, double *fail, double *csig) {
+  orc_apply_bcs_ex(c, geom, cons, prim, temp, c2p_mu, fail, csig, 3);
+}
+// what: bit 0 = the ghost fills (parthenon::ApplyBoundaryConditions), bit 1 = ConvertBoundaryConditions
+void orc_apply_bcs_ex(const orc_cfg *c, const double *geom, double *cons, double *prim, double *temp,
+                      double *c2p_mu, double *fail, double *csig, int what) {
   Lay L(c);
   Geom g(c, geom);
   const long N = L.ncell;
   const int mhd = c->mhd;
   const int lo[3] = {L.is, L.js, L.ks}, hi[3] = {L.ie, L.je, L.ke}, nn[3] = {L.ni, L.nj, L.nk};
-  for (int f = 0; f < 2 * L.ndim; ++f) {
+  for (int f = 0; f < 2 * L.ndim && (what & 1); ++f) {
     const int bc = c->bc[f];
     if (bc <= 0) continue; // 0: inter-block face, -1: periodic mesh face (filled by the halo exchange)
     const int dir = f / 2, outer = f % 2;
@@ -1459,6 +1464,7 @@ void orc_apply_bcs(const orc_cfg *c, const double *geom, double *cons, double *p
         }
     (void)nn;
   }
+  if (!(what & 2)) return;
   // ConvertBoundaryConditions, phoebus_boundaries.cpp:303-448
   // c->bc[f] != 0 marks faces with boundary_flag != block is NOT the same thing: the
   // reference tests "!= block", which also holds for periodic faces. Callers encode periodic

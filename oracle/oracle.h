@@ -104,6 +104,14 @@ void orc_prim_to_cons(const orc_cfg *c, const double *geom, const double *prim, 
  * (phoebus_boundaries.cpp:44-448) for one block */
 void orc_apply_bcs(const orc_cfg *c, const double *geom, double *cons, double *prim,
                    double *temp, double *c2p_mu, double *fail, double *csig);
+/* the two halves of the above separately: what bit 0 = ghost fills, bit 1 = ConvertBoundaryConditions */
+void orc_apply_bcs_ex(const orc_cfg *c, const double *geom, double *cons, double *prim, double *temp,
+                      double *c2p_mu, double *fail, double *csig, int what);
+/* Fishbone-Moncrief torus problem generator (src/pgen/torus.cpp:130-474, IdealGas, u_jitter = 0) on one MeshBlock:
+ * p.* and temperature over the entire block; par as orc_build_geometry, tp = {rin, rmax, kappa, Gamma, nsub, u_jitter} */
+int orc_pgen_torus(const orc_cfg *c, const double *par, const double *tp, const double *geom, double *prim, double *temp);
+/* ComputeBetas (torus.cpp:849-930) over one block's interior: out = {beta_min, bsq_max, press_max} */
+void orc_pgen_betas(const orc_cfg *c, const double *geom, const double *prim, double rho_min_bnorm, double out[3]);
 /* fluid::EstimateTimestepBlock (fluid.cpp:899-944) without the cfl factor */
 double orc_estimate_dt(const orc_cfg *c, const double *csig, const double *fsig,
                        int has_face_speeds);

@@ -4,9 +4,11 @@
 // (src/geometry/cached_system.hpp:593-775). See oracle.h.
 #include "oracle.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <vector>
 
 namespace {
 typedef double Real;
@@ -318,5 +320,263 @@ void orc_build_geometry(int kind, const double *par, const orc_cfg *c, double *g
                 for (int n = m; n < 4; ++n) dtab[(3 + 3 * FLAT[m][n] + (s - 1)) * gcell] = p.dg[m][n][s];
           }
         }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fishbone-Moncrief torus problem generator, src/pgen/torus.cpp:130-474 (IdealGas, no radiation): one MeshBlock,
+// zone by zone as the reference's three kernels do. prim [nprim][k][j][i] and temp are written over the ENTIRE block;
+// the caller continues with orc_prim_to_cons + orc_apply_floors (torus.cpp:471-474).
+// tp = {rin, rmax, kappa, Gamma, nsub, u_jitter}; u_jitter must be 0 (the reference's RNG stream is not restated).
+int orc_pgen_torus(const orc_cfg *c, const double *par, const double *tp, const double *geom, double *prim, double *temp) {
+  const int ng = c->ng, ndim = c->ndim, mhd = c->mhd;
+  const int ni = c->nx[0] + 2 * ng, nj = ndim >= 2 ? c->nx[1] + 2 * ng : 1, nk = ndim >= 3 ? c->nx[2] + 2 * ng : 1;
+  const long N = (long)ni * nj * nk;
+  const int nprim = 7 + 3 * mhd, prs = mhd ? 8 : 5, gm1i = mhd ? 9 : 6;
+  const Real a = par[0], rin = tp[0], rmax = tp[1], kappa = tp[2], gam = tp[3], u_jitter = tp[5];
+  const int nsub = (int)tp[4];
+  if (u_jitter != 0.0 || ndim < 2) return -1;
+  // geom.Lapse(0, x1, x2, x3) etc. on the CACHED system interpolate the cell-centred tables linearly:
+  // cached_system.hpp:132-139,150-155,229-236 with phoebus_interpolation.hpp:122-219 (LCInterp)
+  const long gcellI = (long)c->gk * c->gj * c->gi;
+  auto GetWeights = [&](int d, const Real x, const int nx, int &ix, Real w[2]) {
+    const Real min = c->xmin[d] + (0 + 0.5) * c->dx[d];
+    const Real dx = c->dx[d];
+    ix = std::min(std::max(0, static_cast<int>(ratio(x - min, dx))), nx - 2);
+    const Real floor = min + ix * dx;
+    w[1] = ratio(x - floor, dx);
+    w[0] = 1. - w[1];
+  };
+  auto LCInterp = [&](int v, Real X1, Real X2, Real X3) {
+    auto p = [&](int kk, int jj, int ii) { return geom[(long)v * gcellI + ((long)kk * c->gj + jj) * c->gi + ii]; };
+    if (c->gk > 1) {
+      int ix[3];
+      Real w[3][2];
+      GetWeights(0, X1, c->gi, ix[0], w[0]);
+      GetWeights(1, X2, c->gj, ix[1], w[1]);
+      GetWeights(2, X3, c->gk, ix[2], w[2]);
+      return (w[2][0] * (w[1][0] * (w[0][0] * p(ix[2], ix[1], ix[0]) + w[0][1] * p(ix[2], ix[1], ix[0] + 1)) +
+                         w[1][1] * (w[0][0] * p(ix[2], ix[1] + 1, ix[0]) + w[0][1] * p(ix[2], ix[1] + 1, ix[0] + 1))) +
+              w[2][1] * (w[1][0] * (w[0][0] * p(ix[2] + 1, ix[1], ix[0]) + w[0][1] * p(ix[2] + 1, ix[1], ix[0] + 1)) +
+                         w[1][1] * (w[0][0] * p(ix[2] + 1, ix[1] + 1, ix[0]) + w[0][1] * p(ix[2] + 1, ix[1] + 1, ix[0] + 1))));
+    }
+    int ix1, ix2;
+    Real w1[2], w2[2];
+    GetWeights(0, X1, c->gi, ix1, w1);
+    GetWeights(1, X2, c->gj, ix2, w2);
+    return (w2[0] * (w1[0] * p(0, ix2, ix1) + w1[1] * p(0, ix2, ix1 + 1)) +
+            w2[1] * (w1[0] * p(0, ix2 + 1, ix1) + w1[1] * p(0, ix2 + 1, ix1 + 1)));
+  };
+  Real trp[10];
+  std::memcpy(trp, par, sizeof(trp));
+  trp[6] = 1000.; // McKinneyGammieRyan's six-argument constructor, mckinney_gammie_ryan.hpp:58-62 (torus.cpp:244)
+  trp[7] = 4.0;
+  trp[8] = 4.0;
+  const MGR tr(trp);
+  auto bl_metric = [&](Real X1, Real X2, Real g[4][4]) { // boyer_lindquist.hpp:79-95,262-280
+    const Real a2_ = a * a;
+    const Real r = std::abs(X1), th = X2;
+    const Real sth = std::sin(th), cth = std::cos(th);
+    const Real r2 = r * r, r3 = r2 * r;
+    const Real DD = 1. - ratio(2., r) + ratio(a2_, r2);
+    const Real mu = 1. + ratio(a2_ * cth * cth, r2);
+    const Real sth2 = sth * sth;
+    std::memset(g, 0, 16 * sizeof(Real));
+    g[0][0] = -(1.0 - ratio(2.0, r * mu));
+    g[0][3] = g[3][0] = -ratio(2.0 * a * sth2, r * mu);
+    g[1][1] = mu / DD;
+    g[2][2] = r2 * mu;
+    g[3][3] = r2 * sth2 * (1.0 + ratio(a2_, r2) + ratio(2.0 * a2_ * sth2, r3 * mu));
+  };
+  auto lfish_calc = [](Real r, Real a) { // torus.cpp:745-757
+    return (((std::pow(a, 2) - 2. * a * std::sqrt(r) + std::pow(r, 2)) *
+             ((-2. * a * r * (std::pow(a, 2) - 2. * a * std::sqrt(r) + std::pow(r, 2))) /
+                  std::sqrt(2. * a * std::sqrt(r) + (-3. + r) * r) +
+              ((a + (-2. + r) * std::sqrt(r)) * (std::pow(r, 3) + std::pow(a, 2) * (2. + r))) /
+                  std::sqrt(1 + (2. * a) / std::pow(r, 1.5) - 3. / r))) /
+            (std::pow(r, 3) * std::sqrt(2. * a * std::sqrt(r) + (-3. + r) * r) * (std::pow(a, 2) + (-2. + r) * r)));
+  };
+  auto log_enthalpy = [](const Real r, const Real th, const Real a, const Real rin, const Real l, Real &uphi) { // :759-797
+    const Real sth = sin(th);
+    const Real cth = cos(th);
+    const Real DD = r * r - 2. * r + a * a;
+    const Real AA = (r * r + a * a) * (r * r + a * a) - DD * a * a * sth * sth;
+    const Real SS = r * r + a * a * cth * cth;
+    const Real thin = M_PI / 2.;
+    const Real sthin = sin(thin);
+    const Real cthin = cos(thin);
+    const Real DDin = rin * rin - 2. * rin + a * a;
+    const Real AAin = (rin * rin + a * a) * (rin * rin + a * a) - DDin * a * a * sthin * sthin;
+    const Real SSin = rin * rin + a * a * cthin * cthin;
+    uphi = 0.0;
+    const Real lnh =
+        0.5 * std::log((1. + std::sqrt(1. + 4. * (l * l * SS * SS) * DD / (AA * AA * sth * sth))) / (SS * DD / AA)) -
+        0.5 * std::sqrt(1. + 4. * (l * l * SS * SS) * DD / (AA * AA * sth * sth)) - 2. * a * r * l / AA -
+        (0.5 * std::log((1. + std::sqrt(1. + 4. * (l * l * SSin * SSin) * DDin / (AAin * AAin * sthin * sthin))) /
+                        (SSin * DDin / AAin)) -
+         0.5 * std::sqrt(1. + 4. * (l * l * SSin * SSin) * DDin / (AAin * AAin * sthin * sthin)) - 2. * a * rin * l / AAin);
+    if (lnh > 0.0) {
+      Real expm2chi = SS * SS * DD / (AA * AA * sth * sth);
+      Real up1 = std::sqrt((-1. + std::sqrt(1. + 4. * l * l * expm2chi)) / 2.);
+      uphi = 2. * a * r * std::sqrt(1. + up1 * up1) / std::sqrt(AA * SS * DD) + std::sqrt(SS / AA) * up1 / sth;
+    }
+    return lnh;
+  };
+  auto state = [&](Real hm1, Real rho_rmax, Real &rho_out, Real &u_out) { // GetStateFromEnthalpy, :803-812
+    rho_out = std::pow(hm1 * (gam - 1.) / (kappa * gam), 1. / (gam - 1.));
+    u_out = kappa * std::pow(rho_out, gam) / (gam - 1.) / rho_rmax;
+    rho_out /= rho_rmax;
+  };
+  auto ucon_norm = [](Real ucon[4], Real gcov[4][4]) { // :834-847
+    Real AA = gcov[0][0];
+    Real BB = 2. * (gcov[0][1] * ucon[1] + gcov[0][2] * ucon[2] + gcov[0][3] * ucon[3]);
+    Real CC = 1. + gcov[1][1] * ucon[1] * ucon[1] + gcov[2][2] * ucon[2] * ucon[2] + gcov[3][3] * ucon[3] * ucon[3] +
+              2. * (gcov[1][2] * ucon[1] * ucon[2] + gcov[1][3] * ucon[1] * ucon[3] + gcov[2][3] * ucon[2] * ucon[3]);
+    Real discr = BB * BB - 4. * AA * CC;
+    return (-BB - std::sqrt(discr)) / (2. * AA);
+  };
+  auto floors = [&](Real x1, Real &rflr, Real &sflr) { // Floors::GetFloors, fixup.hpp:92-134 (x1-dependent types)
+    switch (c->floor_type) {
+    case 0: rflr = c->rho0; sflr = c->sie0; break;
+    case 1: rflr = c->rho0 * std::exp(c->rexp * x1); sflr = c->sie0 * std::exp(c->sexp * x1); break;
+    case 2: { Real scratch = c->rho0 * std::exp(c->rexp * x1); sflr = c->sie0 * std::exp(c->sexp * x1) / std::max(rflr, scratch); rflr = scratch; } break;
+    default: rflr = c->rho0 * std::min(1.0, std::pow(x1, c->rexp)); sflr = c->sie0 * std::min(1.0, std::pow(x1, c->sexp)); break;
+    }
+    rflr = std::max(rflr, c->rho_min_eos);
+    sflr = std::max(sflr, c->sie_min_eos);
+  };
+  const Real angular_mom = lfish_calc(rmax, a);
+  Real uphi_rmax;
+  const Real hm1_rmax = std::exp(log_enthalpy(rmax, 0.5 * M_PI, a, rin, angular_mom, uphi_rmax)) - 1.0;
+  Real rho_rmax, u_rmax;
+  state(hm1_rmax, 1.0, rho_rmax, u_rmax);
+  auto V = [&](int n, int k, int j, int i) -> double & { return prim[(long)n * N + ((long)k * nj + j) * ni + i]; };
+  for (long q = 0; q < (long)nprim * N; ++q) prim[q] = 0.0;
+  for (int k = 0; k < nk; ++k)
+    for (int j = 0; j < nj; ++j)
+      for (int i = 0; i < ni; ++i) {
+        const Real dx_sub = c->dx[0] / nsub, dy_sub = c->dx[1] / nsub;
+        const Real x3 = c->xmin[2] + (k + 0.5) * c->dx[2];
+        for (int m = 0; m < nsub; m++)
+          for (int n = 0; n < nsub; n++) {
+            const Real x1 = (c->xmin[0] + i * c->dx[0]) + (m + 0.5) * dx_sub;
+            const Real x2 = (c->xmin[1] + j * c->dx[1]) + (n + 0.5) * dy_sub;
+            Real y, th;
+            const Real r = tr.r_(x1);
+            tr.th_(x1, x2, y, th);
+            Real lnh = -1.0, uphi;
+            if (r > rin) lnh = log_enthalpy(r, th, a, rin, angular_mom, uphi);
+            if (lnh > 0.0) {
+              Real hm1 = std::exp(lnh) - 1.;
+              Real rho, u;
+              state(hm1, rho_rmax, rho, u);
+              Real ucon_bl[] = {0.0, 0.0, 0.0, uphi};
+              Real gcov[4][4];
+              bl_metric(r, th, gcov);
+              ucon_bl[0] = ucon_norm(ucon_bl, gcov);
+              // bl_to_fmks, mckinney_gammie_ryan.hpp:119-151
+              Real trans[4][4], ucon_ks[4] = {0, 0, 0, 0}, ucon[4] = {0, 0, 0, 0};
+              std::memset(trans, 0, sizeof(trans));
+              const Real idenom = 1.0 / (r * r - 2.0 * r + a * a);
+              trans[0][0] = 1.0;
+              trans[0][1] = 2.0 * r * idenom;
+              trans[1][1] = 1.0;
+              trans[2][2] = 1.0;
+              trans[3][1] = a * idenom;
+              trans[3][3] = 1.0;
+              for (int mu = 0; mu < 4; ++mu)
+                for (int nu = 0; nu < 4; ++nu) ucon_ks[mu] += trans[mu][nu] * ucon_bl[nu];
+              Real C[3], Jcov[3][3], Jcon[3][3];
+              tr(x1, x2, x3, C, Jcov, Jcon);
+              std::memset(trans, 0, sizeof(trans));
+              trans[0][0] = 1.0;
+              for (int p = 0; p < 3; ++p)
+                for (int qq = 0; qq < 3; ++qq) trans[p + 1][qq + 1] = Jcon[p][qq];
+              for (int mu = 0; mu < 4; ++mu)
+                for (int nu = 0; nu < 4; ++nu) ucon[mu] += trans[mu][nu] * ucon_ks[nu];
+              const Real lapse = LCInterp(0, x1, x2, x3);
+              Real beta[3];
+              for (int d = 0; d < 3; ++d) beta[d] = LCInterp(1 + d, x1, x2, x3);
+              for (int mu = 0; mu < 4; ++mu)
+                for (int nu = 0; nu < 4; ++nu) gcov[mu][nu] = LCInterp(4 + FLAT[mu][nu], x1, x2, x3);
+              ucon[0] = ucon_norm(ucon, gcov);
+              const Real W = lapse * ucon[0];
+              Real vcon[] = {ucon[1] / W + beta[0] / lapse, ucon[2] / W + beta[1] / lapse, ucon[3] / W + beta[2] / lapse};
+              V(0, k, j, i) += rho / (nsub * nsub);
+              V(4, k, j, i) += u / (nsub * nsub);
+              for (int d = 0; d < 3; d++) V(1 + d, k, j, i) += W * vcon[d] / (nsub * nsub);
+            }
+          }
+        const Real x1v = c->xmin[0] + (i + 0.5) * c->dx[0];
+        V(4, k, j, i) *= (1. + u_jitter * (0.5 - 0.5));
+        Real rhoflr = 0, epsflr;
+        floors(x1v, rhoflr, epsflr);
+        V(0, k, j, i) = V(0, k, j, i) < rhoflr ? rhoflr : V(0, k, j, i);
+        V(4, k, j, i) = V(4, k, j, i) / V(0, k, j, i) < epsflr ? V(0, k, j, i) * epsflr : V(4, k, j, i);
+        // IdealGas in scale-free units, eos_ideal.hpp:59-137
+        const Real T = std::max(0.0, (V(4, k, j, i) / V(0, k, j, i)) / c->Cv);
+        temp[((long)k * nj + j) * ni + i] = T;
+        V(prs, k, j, i) = std::max(0.0, c->gm1 * V(0, k, j, i) * c->Cv * T);
+        V(gm1i, k, j, i) = std::max(0.0, (c->gm1 + 1) * c->gm1 * V(0, k, j, i) * c->Cv * T) / V(prs, k, j, i);
+      }
+  if (!mhd) return 0;
+  // vector potential at the corners, from the density of plane kb.s of the entire domain (torus.cpp:435-451)
+  std::vector<Real> A((size_t)nj * ni, 0.0);
+  for (int j = 1; j <= nj - 1; ++j)
+    for (int i = 1; i <= ni - 1; ++i) {
+      const Real rho_av = 0.25 * (V(0, 0, j, i) + V(0, 0, j, i - 1) + V(0, 0, j - 1, i) + V(0, 0, j - 1, i - 1));
+      const Real q = rho_av - 0.2;
+      A[(size_t)j * ni + i] = (q > 0 ? q : 0.0);
+    }
+  const long gcell = (long)c->gk * c->gj * c->gi;
+  for (int k = 0; k < nk; ++k)
+    for (int j = 0; j <= nj - 2; ++j)
+      for (int i = 0; i <= ni - 2; ++i) {
+        const long gc = ((long)(c->gk == 1 ? 0 : k) * c->gj + (c->gj == 1 ? 0 : j)) * c->gi + (c->gi == 1 ? 0 : i);
+        const Real gamdet = geom[(long)20 * gcell + gc]; // loc 0 (Cent), component detgam
+        auto Aa = [&](int jj, int ii) { return A[(size_t)jj * ni + ii]; };
+        V(5, k, j, i) = -(Aa(j, i) - Aa(j + 1, i) + Aa(j, i + 1) - Aa(j + 1, i + 1)) / (2.0 * c->dx[1] * gamdet);
+        V(6, k, j, i) = (Aa(j, i) + Aa(j + 1, i) - Aa(j, i + 1) - Aa(j + 1, i + 1)) / (2.0 * c->dx[0] * gamdet);
+        V(7, k, j, i) = 0.0;
+      }
+  return 0;
+}
+
+// ComputeBetas, torus.cpp:849-930, one MeshBlock's interior: out = {beta_min, bsq_max, press_max}
+void orc_pgen_betas(const orc_cfg *c, const double *geom, const double *prim, double rho_min_bnorm, double out[3]) {
+  const int ng = c->ng, ndim = c->ndim;
+  const int ni = c->nx[0] + 2 * ng, nj = ndim >= 2 ? c->nx[1] + 2 * ng : 1, nk = ndim >= 3 ? c->nx[2] + 2 * ng : 1;
+  const long N = (long)ni * nj * nk;
+  const long gcell = (long)c->gk * c->gj * c->gi;
+  Real beta_min = std::numeric_limits<Real>::infinity(), press_max = -beta_min, bsq_max = -beta_min;
+  for (int k = (ndim >= 3 ? ng : 0); k < (ndim >= 3 ? nk - ng : 1); ++k)
+    for (int j = (ndim >= 2 ? ng : 0); j < (ndim >= 2 ? nj - ng : 1); ++j)
+      for (int i = ng; i < ni - ng; ++i) {
+        const long o = ((long)k * nj + j) * ni + i;
+        const long gc = ((long)(c->gk == 1 ? 0 : k) * c->gj + (c->gj == 1 ? 0 : j)) * c->gi + (c->gi == 1 ? 0 : i);
+        Real gcov[3][3];
+        for (int m = 0; m < 3; ++m)
+          for (int n = 0; n < 3; ++n) gcov[m][n] = geom[(long)(4 + FLAT[m + 1][n + 1]) * gcell + gc];
+        const Real vp[3] = {prim[1 * N + o], prim[2 * N + o], prim[3 * N + o]};
+        const Real Bp[3] = {prim[5 * N + o], prim[6 * N + o], prim[7 * N + o]};
+        Real vsq = 0.;
+        for (int m = 0; m < 3; ++m)
+          for (int n = 0; n < 3; ++n) vsq += gcov[m][n] * vp[m] * vp[n];
+        const Real W = std::sqrt(1. + vsq);
+        Real Bsq = 0, Bdotv = 0; // relativity_utils.hpp:131-141
+        for (int m = 0; m < 3; ++m)
+          for (int n = 0; n < 3; ++n) {
+            Bdotv += gcov[m][n] * ratio(vp[m], W) * Bp[n];
+            Bsq += gcov[m][n] * Bp[m] * Bp[n];
+          }
+        const Real bsq = ratio(Bsq, W * W) + Bdotv * Bdotv;
+        const Real P = prim[8 * N + o];
+        const Real beta = ratio(P, 0.5 * bsq);
+        if (prim[o] > rho_min_bnorm && beta < beta_min) beta_min = beta;
+        bsq_max = std::max(bsq, bsq_max);
+        press_max = std::max(P, press_max);
+      }
+  out[0] = beta_min;
+  out[1] = bsq_max;
+  out[2] = press_max;
 }
 }

@@ -109,6 +109,10 @@ def lib():
     L.orc_apply_floors.argtypes = [cp, dp, dp, dp, dp, dp, dp, C.c_void_p]
     L.orc_prim_to_cons.argtypes = [cp, dp, dp, dp, dp, ip2, ip2, ip2]
     L.orc_apply_bcs.argtypes = [cp, dp, dp, dp, dp, dp, dp, dp]
+    L.orc_apply_bcs_ex.argtypes = [cp, dp, dp, dp, dp, dp, dp, dp, C.c_int]
+    L.orc_pgen_torus.argtypes = [cp, dp, dp, dp, dp, dp]
+    L.orc_pgen_torus.restype = C.c_int
+    L.orc_pgen_betas.argtypes = [cp, dp, dp, C.c_double, dp]
     L.orc_estimate_dt.argtypes = [cp, dp, dp, C.c_int]
     L.orc_estimate_dt.restype = C.c_double
     L.orc_recon5.argtypes = [C.c_int, dp, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -79,6 +79,12 @@ SYMBOLS = {
     "pb_halo_pack": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P, _P]),
     "pb_halo_unpack": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P, _P]),
     "pb_apply_bcs": (C.c_int, [_PACK, _CFG, _P, _P]),
+    "pb_apply_bcs_ex": (C.c_int, [_PACK, _CFG, _P, C.c_int, _P]),
+    "pb_pgen_torus_table_host": (C.c_int, [_D3, _D3, _CFG, _D3, _D3, _P, _P]),
+    "pb_pgen_torus_fill": (C.c_int, [_PACK, _CFG, _P, C.c_double, C.c_ulonglong, _P]),
+    "pb_pgen_torus_bfield": (C.c_int, [_PACK, _CFG, _P]),
+    "pb_pgen_betas": (C.c_int, [_PACK, _CFG, C.c_double, _P, _D3, _P]),
+    "pb_scale_bfield": (C.c_int, [_PACK, _CFG, C.c_double, _P]),
     "pb_calculate_divb": (C.c_int, [_PACK, _CFG, _P, _P, _P]),
     "pb_history_fluid": (C.c_int, [_PACK, _CFG, _P, _P, _D3, _P]),
     "pb_history_torus": (C.c_int, [_PACK, _CFG, _P, C.c_double, C.c_double, _P, _D3, _P]),

@@ -301,3 +301,205 @@ extern "C" int pb_build_floor_table_host(const pb_cfg_t *c, const double xmin[3]
     }
   return PB_OK;
 }
+
+// ================================================================================================
+// Fishbone-Moncrief torus, ref: src/pgen/torus.cpp:130-362,745-833 (IdealGas branch). The solution is
+// axisymmetric and made of log / exp / pow / sin / cos, so — like the metric — it is tabulated on the HOST
+// with glibc in the reference's evaluation order, one (j, i) table per MeshBlock column; the device side
+// (pgen_kernels.cu) broadcasts it along x3 and does the rest (jitter, floors, EOS, vector potential, B).
+namespace {
+// ref: src/geometry/boyer_lindquist.hpp:79-95,262-280
+void bl_metric4(Real a, Real X1, Real X2, Real g[4][4]) {
+  const Real a2 = a * a;
+  const Real r = std::abs(X1), th = X2;
+  const Real sth = std::sin(th), cth = std::cos(th);
+  const Real r2 = r * r, r3 = r2 * r;
+  const Real DD = 1. - ratio(2., r) + ratio(a2, r2);
+  const Real mu = 1. + ratio(a2 * cth * cth, r2);
+  const Real sth2 = sth * sth;
+  std::memset(g, 0, 16 * sizeof(Real));
+  g[0][0] = -(1.0 - ratio(2.0, r * mu));
+  g[0][3] = g[3][0] = -ratio(2.0 * a * sth2, r * mu);
+  g[1][1] = mu / DD;
+  g[2][2] = r2 * mu;
+  g[3][3] = r2 * sth2 * (1.0 + ratio(a2, r2) + ratio(2.0 * a2 * sth2, r3 * mu));
+}
+// ref: torus.cpp:745-757
+Real lfish_calc(Real r, Real a) {
+  return (((std::pow(a, 2) - 2. * a * std::sqrt(r) + std::pow(r, 2)) *
+           ((-2. * a * r * (std::pow(a, 2) - 2. * a * std::sqrt(r) + std::pow(r, 2))) / std::sqrt(2. * a * std::sqrt(r) + (-3. + r) * r) +
+            ((a + (-2. + r) * std::sqrt(r)) * (std::pow(r, 3) + std::pow(a, 2) * (2. + r))) / std::sqrt(1 + (2. * a) / std::pow(r, 1.5) - 3. / r))) /
+          (std::pow(r, 3) * std::sqrt(2. * a * std::sqrt(r) + (-3. + r) * r) * (std::pow(a, 2) + (-2. + r) * r)));
+}
+// ref: torus.cpp:759-797
+Real log_enthalpy(const Real r, const Real th, const Real a, const Real rin, const Real l, Real &uphi) {
+  const Real sth = sin(th);
+  const Real cth = cos(th);
+  const Real DD = r * r - 2. * r + a * a;
+  const Real AA = (r * r + a * a) * (r * r + a * a) - DD * a * a * sth * sth;
+  const Real SS = r * r + a * a * cth * cth;
+  const Real thin = M_PI / 2.;
+  const Real sthin = sin(thin);
+  const Real cthin = cos(thin);
+  const Real DDin = rin * rin - 2. * rin + a * a;
+  const Real AAin = (rin * rin + a * a) * (rin * rin + a * a) - DDin * a * a * sthin * sthin;
+  const Real SSin = rin * rin + a * a * cthin * cthin;
+  uphi = 0.0;
+  const Real lnh = 0.5 * std::log((1. + std::sqrt(1. + 4. * (l * l * SS * SS) * DD / (AA * AA * sth * sth))) / (SS * DD / AA)) -
+                   0.5 * std::sqrt(1. + 4. * (l * l * SS * SS) * DD / (AA * AA * sth * sth)) - 2. * a * r * l / AA -
+                   (0.5 * std::log((1. + std::sqrt(1. + 4. * (l * l * SSin * SSin) * DDin / (AAin * AAin * sthin * sthin))) /
+                                   (SSin * DDin / AAin)) -
+                    0.5 * std::sqrt(1. + 4. * (l * l * SSin * SSin) * DDin / (AAin * AAin * sthin * sthin)) - 2. * a * rin * l / AAin);
+  if (lnh > 0.0) {
+    Real expm2chi = SS * SS * DD / (AA * AA * sth * sth);
+    Real up1 = std::sqrt((-1. + std::sqrt(1. + 4. * l * l * expm2chi)) / 2.);
+    uphi = 2. * a * r * std::sqrt(1. + up1 * up1) / std::sqrt(AA * SS * DD) + std::sqrt(SS / AA) * up1 / sth;
+  }
+  return lnh;
+}
+// ref: torus.cpp:803-812 (IdealGas)
+void state_from_enthalpy(Real hm1, Real kappa, Real gam, Real rho_rmax, Real &rho_out, Real &u_out) {
+  rho_out = std::pow(hm1 * (gam - 1.) / (kappa * gam), 1. / (gam - 1.));
+  u_out = kappa * std::pow(rho_out, gam) / (gam - 1.) / rho_rmax;
+  rho_out /= rho_rmax;
+}
+// ref: torus.cpp:834-847; returns false where the reference aborts (discr < 0)
+bool ucon_norm(const Real ucon[4], const Real gcov[4][4], Real &u0) {
+  Real AA = gcov[0][0];
+  Real BB = 2. * (gcov[0][1] * ucon[1] + gcov[0][2] * ucon[2] + gcov[0][3] * ucon[3]);
+  Real CC = 1. + gcov[1][1] * ucon[1] * ucon[1] + gcov[2][2] * ucon[2] * ucon[2] + gcov[3][3] * ucon[3] * ucon[3] +
+            2. * (gcov[1][2] * ucon[1] * ucon[2] + gcov[1][3] * ucon[1] * ucon[3] + gcov[2][3] * ucon[2] * ucon[3]);
+  Real discr = BB * BB - 4. * AA * CC;
+  if (discr < 0) return false;
+  u0 = (-BB - std::sqrt(discr)) / (2. * AA);
+  return true;
+}
+} // namespace
+
+namespace {
+// The pgen reads the metric through the CACHED system's coordinate accessors (geom.Lapse(0, x1, x2, x3) ...), which
+// interpolate the cell-centred tables linearly (ref: src/geometry/cached_system.hpp:132-139,150-155,229-236,
+// src/phoebus_utils/phoebus_interpolation.hpp:122-219): at a cell centre the weights are (1, 0) up to the rounding of
+// the coordinate arithmetic, which is where the last-bit structure of the reference's initial velocities comes from.
+struct CentInterp {
+  const double *tab; // one slot of the geometry table
+  int gk, gj, gi;
+  const double *xmin, *dx;
+  void weights(int d, Real x, int nx, int &ix, Real w[2]) const {
+    const Real mn = xmin[d] + (0 + 0.5) * dx[d]; // Xc<d>(0)
+    ix = std::min(std::max(0, static_cast<int>(ratio(x - mn, dx[d]))), nx - 2);
+    const Real fl = mn + ix * dx[d];
+    w[1] = ratio(x - fl, dx[d]);
+    w[0] = 1. - w[1];
+  }
+  Real operator()(int comp, Real X1, Real X2, Real X3) const { // comp: index into the Cent block of the table
+    const long gcell = (long)gk * gj * gi;
+    const double *p = tab + (long)comp * gcell;
+    auto P = [&](int k, int j, int i) { return p[((long)k * gj + j) * gi + i]; };
+    if (gk > 1) {
+      int ix[3];
+      Real w[3][2];
+      weights(0, X1, gi, ix[0], w[0]);
+      weights(1, X2, gj, ix[1], w[1]);
+      weights(2, X3, gk, ix[2], w[2]);
+      return (w[2][0] * (w[1][0] * (w[0][0] * P(ix[2], ix[1], ix[0]) + w[0][1] * P(ix[2], ix[1], ix[0] + 1)) +
+                         w[1][1] * (w[0][0] * P(ix[2], ix[1] + 1, ix[0]) + w[0][1] * P(ix[2], ix[1] + 1, ix[0] + 1))) +
+              w[2][1] * (w[1][0] * (w[0][0] * P(ix[2] + 1, ix[1], ix[0]) + w[0][1] * P(ix[2] + 1, ix[1], ix[0] + 1)) +
+                         w[1][1] * (w[0][0] * P(ix[2] + 1, ix[1] + 1, ix[0]) + w[0][1] * P(ix[2] + 1, ix[1] + 1, ix[0] + 1))));
+    }
+    int ix1, ix2;
+    Real w1[2], w2[2];
+    weights(0, X1, gi, ix1, w1);
+    weights(1, X2, gj, ix2, w2);
+    return (w2[0] * (w1[0] * P(0, ix2, ix1) + w1[1] * P(0, ix2, ix1 + 1)) +
+            w2[1] * (w1[0] * P(0, ix2 + 1, ix1) + w1[1] * P(0, ix2 + 1, ix1 + 1)));
+  }
+};
+} // namespace
+
+// torus_par = {rin, rmax, kappa, Gamma, nsub}; geom_tab = this MeshBlock column's geometry table (pb_build_geometry_host);
+// out_host[5][tk][nj][ni] = rho, u, W v^1, W v^2, W v^3 of the torus interior (0 outside), before jitter and floors;
+// tk = 1 for an axisymmetric (2-D) geometry table, else nk.
+extern "C" int pb_pgen_torus_table_host(const double *geom_par, const double *torus_par, const pb_cfg_t *cfg,
+                                        const double xmin[3], const double dx[3], const double *geom_tab, double *out) {
+  if (!geom_par || !torus_par || !cfg || !out || !geom_tab) return PB_EINVAL;
+  if (cfg->gj < 2 || cfg->gi < 2) return PB_EINVAL; // FMKS tables are at least 2-D
+  const Real a = geom_par[0], rin = torus_par[0], rmax = torus_par[1], kappa = torus_par[2], gam = torus_par[3];
+  const int nsub = (int)torus_par[4];
+  if (nsub < 1) return PB_EINVAL;
+  const int ni = cfg->nx[0] + 2 * cfg->ng, nj = cfg->ndim >= 2 ? cfg->nx[1] + 2 * cfg->ng : 1;
+  const int tk = cfg->gk > 1 ? cfg->gk : 1;
+  const CentInterp geom{geom_tab, cfg->gk, cfg->gj, cfg->gi, xmin, dx};
+  // the pgen's own coordinate map: the six-argument constructor, i.e. hexp_br = 1000, nsq = csq = 4
+  // (ref: torus.cpp:244, mckinney_gammie_ryan.hpp:57-62)
+  Real tr_par[10];
+  std::memcpy(tr_par, geom_par, sizeof(tr_par));
+  tr_par[6] = 1000.;
+  tr_par[7] = 4.0;
+  tr_par[8] = 4.0;
+  const FmksMap tr(tr_par);
+  const Real angular_mom = lfish_calc(rmax, a);
+  Real uphi_rmax;
+  const Real hm1_rmax = std::exp(log_enthalpy(rmax, 0.5 * M_PI, a, rin, angular_mom, uphi_rmax)) - 1.0;
+  Real rho_rmax, u_rmax;
+  state_from_enthalpy(hm1_rmax, kappa, gam, 1.0, rho_rmax, u_rmax);
+  const long N = (long)ni * nj * tk;
+  int bad = 0;
+#pragma omp parallel for collapse(2) schedule(static) reduction(+ : bad)
+  for (int k = 0; k < tk; ++k)
+  for (int j = 0; j < nj; ++j)
+    for (int i = 0; i < ni; ++i) {
+      const Real dx_sub = dx[0] / nsub, dy_sub = dx[1] / nsub;
+      Real acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      const Real x3 = xmin[2] + (k + 0.5) * dx[2];
+      for (int m = 0; m < nsub; m++)
+        for (int n = 0; n < nsub; n++) {
+          const Real x1 = (xmin[0] + i * dx[0]) + (m + 0.5) * dx_sub;
+          const Real x2 = (xmin[1] + j * dx[1]) + (n + 0.5) * dy_sub;
+          Real C[3], J[3][3], Ji[3][3];
+          tr.eval(x1, x2, x3, C, J, Ji);
+          const Real r = C[0], th = C[1];
+          Real lnh = -1.0, uphi;
+          if (r > rin) lnh = log_enthalpy(r, th, a, rin, angular_mom, uphi);
+          if (lnh > 0.0) {
+            const Real hm1 = std::exp(lnh) - 1.;
+            Real rho, u;
+            state_from_enthalpy(hm1, kappa, gam, rho_rmax, rho, u);
+            Real ucon_bl[4] = {0.0, 0.0, 0.0, uphi};
+            Real gcov[4][4];
+            bl_metric4(a, r, th, gcov);
+            if (!ucon_norm(ucon_bl, gcov, ucon_bl[0])) bad++;
+            // bl_to_ks then KS -> FMKS with the inverse Jacobian, ref: mckinney_gammie_ryan.hpp:119-151
+            Real trans[4][4] = {{0}}, ucon_ks[4] = {0, 0, 0, 0}, ucon[4] = {0, 0, 0, 0};
+            const Real idenom = 1.0 / (r * r - 2.0 * r + a * a);
+            trans[0][0] = 1.0;
+            trans[0][1] = 2.0 * r * idenom;
+            trans[1][1] = 1.0;
+            trans[2][2] = 1.0;
+            trans[3][1] = a * idenom;
+            trans[3][3] = 1.0;
+            for (int mu = 0; mu < 4; ++mu)
+              for (int nu = 0; nu < 4; ++nu) ucon_ks[mu] += trans[mu][nu] * ucon_bl[nu];
+            Real t2[4][4] = {{0}};
+            t2[0][0] = 1.0;
+            for (int p = 0; p < 3; ++p)
+              for (int q = 0; q < 3; ++q) t2[p + 1][q + 1] = Ji[p][q];
+            for (int mu = 0; mu < 4; ++mu)
+              for (int nu = 0; nu < 4; ++nu) ucon[mu] += t2[mu][nu] * ucon_ks[nu];
+            const Real lapse = geom(0, x1, x2, x3);
+            Real beta[3];
+            for (int d = 0; d < 3; ++d) beta[d] = geom(1 + d, x1, x2, x3);
+            for (int mu = 0; mu < 4; ++mu)
+              for (int nu = 0; nu < 4; ++nu) gcov[mu][nu] = geom(4 + sym4(mu, nu), x1, x2, x3);
+            if (!ucon_norm(ucon, gcov, ucon[0])) bad++;
+            const Real W = lapse * ucon[0];
+            const Real vcon[3] = {ucon[1] / W + beta[0] / lapse, ucon[2] / W + beta[1] / lapse, ucon[3] / W + beta[2] / lapse};
+            acc[0] += rho / (nsub * nsub);
+            acc[1] += u / (nsub * nsub);
+            for (int d = 0; d < 3; d++) acc[2 + d] += W * vcon[d] / (nsub * nsub);
+          }
+        }
+      for (int q = 0; q < 5; ++q) out[q * N + ((long)k * nj + j) * ni + i] = acc[q];
+    }
+  return bad ? PB_EINVAL : PB_OK; // discr < 0: the reference aborts ("discr < 0")
+}

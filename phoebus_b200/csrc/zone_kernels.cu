@@ -639,8 +639,10 @@ __global__ void p2c_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons,
 // reference's order x1, x2, x3), which makes the fill race-free and single-launch. The conversion
 // (inflow check, p2c of the prim-filled ghosts) is pointwise and follows in the same thread.
 template <bool MHD>
+// what: bit 0 = ghost fill, bit 1 = ConvertBoundaryConditions (pb_apply_bcs does both; Mesh::Initialize's
+// CommunicateBoundaries fills without converting, external/parthenon/src/mesh/mesh.cpp:692-706).
 __global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const int nlist,
-                                                    unsigned long long *err_count) {
+                                                    unsigned long long *err_count, const int what) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   const Lay L(cfg);
   const Shell sh(L);
@@ -670,7 +672,7 @@ __global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const 
   const int o = L.idx(k, j, i);
   const GeomTab gt(cfg, pack.geom, blk.geom_slot);
   const ZonePtr<MHD> z(pack, cons, L, b, o);
-  if (nphys > 0) {
+  if (nphys > 0 && (what & 1)) {
     // source chain: cur[3] = zone read by the x3 step, cur[2] by the x2 step, ...
     int c3[3] = {i, j, k}, c2[3], c1[3], c0[3];
     auto map = [&](int d, const int in[3], int out[3]) {
@@ -711,7 +713,18 @@ __global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const 
       *z.temp = pack.temp[(size_t)b * N + src];
       *z.mu = pack.c2p_mu[(size_t)b * N + src];
       *z.fail = pack.fail[(size_t)b * N + src];
-      // cons are copied too but overwritten by the p2c below (every physical face is "!= block")
+      // cons are copied too (no sqrt(gamma) rescale in primitive mode) but overwritten by the p2c of the conversion
+      // (every physical face is "!= block"): only a fill WITHOUT conversion has to materialise them
+      if (!(what & 2)) {
+        Real U[NCn];
+        load_comps<NCn>(cons + (size_t)b * NCn * N + src, N, U);
+        for (int d = 0; d < 3; ++d) {
+          if (!act[d] || blk.bc[face[d]] != PB_BC_REFLECT) continue;
+          U[CMOM + d] = -1.0 * U[CMOM + d];
+          if (MHD) U[CB + d] = -1.0 * U[CB + d];
+        }
+        store_comps<NCn>(z.cons, N, U);
+      }
     } else {
       Real U[NCn];
       load_comps<NCn>(cons + (size_t)b * NCn * N + src, N, U);
@@ -732,6 +745,7 @@ __global__ void __launch_bounds__(128, 6) bc_kernel(const pb_pack_t pack, const 
     }
   }
   // ---- ConvertBoundaryConditions (pointwise)
+  if (!(what & 2)) return;
   PointGeom g;
   g.load(gt, 0, gt.cell(k, j, i));
   bool did_p2c = false;
@@ -971,8 +985,13 @@ extern "C" int pb_prim_to_cons(const pb_pack_t *pack, const pb_cfg_t *cfg, doubl
 }
 
 extern "C" int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {
+  return pb_apply_bcs_ex(pack, cfg, cons, 3, stream);
+}
+
+extern "C" int pb_apply_bcs_ex(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int what, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
+  if (!cons || (what & 3) == 0) return set_error(PB_EINVAL, "pb_apply_bcs_ex: NULL container or empty task mask");
   const Lay L(*cfg);
   const Shell sh(L);
   const int nlist = pack->bc_blocks ? pack->n_bc_blocks : pack->nblocks;
@@ -980,8 +999,8 @@ extern "C" int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *
   const int T = zone_threads();
   const unsigned grid = grid_for((long long)sh.n * nlist, T);
   cudaStream_t s = (cudaStream_t)stream;
-  if (cfg->mhd) bc_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, nlist, err_counter());
-  else bc_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, nlist, err_counter());
+  if (cfg->mhd) bc_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, nlist, err_counter(), what);
+  else bc_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, nlist, err_counter(), what);
   return check_launch("bc_kernel");
 }
 

@@ -153,6 +153,24 @@ class FluidParams:
             hexp_nsq=g.real("coordinates", "hexp_nsq", 4.0), hexp_csq=g.real("coordinates", "hexp_csq", 4.0),
             derefine_poles=float(g.boolean("coordinates", "derefine_poles", True)))
         self.axisymmetric = g.boolean("geometry", "axisymmetric", False)
+        # ---- <torus> (ref: src/pgen/torus.cpp:176-185,526-531)
+        self.torus = dict(rin=g.real("torus", "rin", 6.0), rmax=g.real("torus", "rmax", 12.0), kappa=g.real("torus", "kappa", 1.e-2),
+                          u_jitter=g.real("torus", "u_jitter", 1.e-2), seed=g.integer("torus", "seed", 0),
+                          nsub=g.integer("torus", "nsub", 1), magnetized=g.boolean("torus", "magnetized", True),
+                          target_beta=g.real("torus", "target_beta", 100.0),
+                          harm_beta_normalization=g.boolean("torus", "harm_beta_normalization", True),
+                          rho_min_bnorm=g.real("torus", "rho_min_bnorm", 1.e-4))
+        # the reference picks the ghost-fill function from <parthenon/mesh> and the FixFluxes branch from <phoebus>
+        # (phoebus_boundaries.cpp:497-505 vs fluid.cpp:178-189); one code per face here, so the two must agree
+        for d in (1, 2, 3):
+            for io in ("i", "o"):
+                key = "%sx%d_bc" % (io, d)
+                parth = g.string("parthenon/mesh", key, "periodic")
+                ph = g.get("phoebus", key)
+                if parth != "periodic" and ph is not None and ph != parth:
+                    raise ValueError("<phoebus>/%s = %s disagrees with <parthenon/mesh>/%s = %s" % (key, ph, key, parth))
+        if any(b == "polar" for b in self.mesh_bc) and not self.bc_prim:
+            raise ValueError("Polar X2 reflecting BCs not supported")  # ref: phoebus_boundaries.cpp:167,199 (bc_vars == primitive)
 
     def geom_par_array(self):
         import numpy as np

@@ -1,14 +1,25 @@
-"""Input producers next to the hot path: the torus problem modifier and a
-synthetic torus-like initial state generated directly in HBM for the benchmark configurations.
+"""Problem generators next to the hot path.
 
-The synthetic state is NOT the Fishbone-Moncrief solution of the reference's torus pgen
-(ref: src/pgen/torus.cpp:130-474); it is a smooth, magnetised, rotating density torus embedded in
-a floor-dominated atmosphere on the same FMKS grid, so that the hot path sees the same mix of
-work (smooth torus zones, floored funnel/atmosphere zones, horizon-crossing inner boundary).
+init_torus: the reference's start-up sequence for the Fishbone-Moncrief torus (`problem = torus`), through the C ABI:
+
+  phoebus::ProblemModifier            torus_problem_modifier (x1 range from r_outer and the horizon, ref: src/pgen/torus.cpp:476-498)
+  Mesh::Initialize                    (ref: external/parthenon/src/mesh/mesh.cpp:745-856)
+    ProblemGenerator                  pb_pgen_torus_table_host (host libm, one table per MeshBlock column) -> pb_pgen_torus_fill ->
+                                      pb_pgen_torus_bfield -> pb_prim_to_cons -> pb_apply_floors   (ref: torus.cpp:130-474)
+    CommunicateBoundaries             ghost exchange + pb_apply_bcs_ex(fill only)   (ref: mesh.cpp:640-707)
+    FillDerived                       pb_cons_to_prim over the entire blocks         (ref: mesh.cpp:725-739)
+  PostInitializationModifier          pb_pgen_betas -> pb_scale_bfield -> pb_prim_to_cons   (ref: torus.cpp:525-737)
+
+The result is bit-identical to the reference's state at the start of its first cycle (tests/test_gpu_parity.py,
+torus2d / torus3d "init" dumps). With torus/u_jitter != 0 the energy jitter comes from a counter-based hash of the
+zone coordinates (the reference's Kokkos RNG stream depends on the thread count and is not reproduced).
 """
+import ctypes as C
 import math
 
 import numpy as np
+
+from . import _lib
 
 
 def torus_problem_modifier(pin):
@@ -29,47 +40,116 @@ def torus_problem_modifier(pin):
     return x1min, x1max
 
 
-def synthetic_torus(mesh, seed_amp=0.02):
-    """Fill mesh.prim (all zones, ghosts included) with a torus-like state, device-side."""
-    t = mesh.torch
+def torus_tables(mesh):
+    """host tables of the torus solution, one per geometry slot (= MeshBlock column): [nslot][5][tk][nj][ni]"""
+    L = _lib.lib()
     p = mesh.p
-    dev = mesh.device
-    gam = p.gamma
-    h = p.geom_par["h"]
-    r0, w = p_get(p, "rmax", 12.0), 4.0
-    kappa = p_get(p, "kappa", 0.01)
+    if mesh.geom_kind != 1:
+        raise ValueError('Problem "torus" requires FMKS geometry!')  # ref: torus.cpp:132-133
+    t = p.torus
+    tpar = np.array([t["rin"], t["rmax"], t["kappa"], p.gamma, float(t["nsub"])], dtype=np.float64)
+    gpar = np.ascontiguousarray(mesh.geom_par, dtype=np.float64)
+    tk = mesh.gshape[0] if mesh.gshape[0] > 1 else 1
+    nslot = mesh.geom_host.shape[0]
+    out = np.zeros((nslot, 5, tk, mesh.nj, mesh.ni))
+    done = set()
+    D = C.POINTER(C.c_double)
     for n in range(mesh.nblocks):
-        x1, x2, x3 = (t.from_numpy(np.ascontiguousarray(a)).to(dev) for a in mesh.cell_centers(n))
-        X1 = x1.view(1, 1, -1)
-        X2 = x2.view(1, -1, 1)
-        X3 = x3.view(-1, 1, 1)
-        r = t.exp(X1)
-        th = math.pi * X2 + ((1.0 - h) / 2.0) * t.sin(2.0 * math.pi * X2)
-        s = t.sin(th).abs()
-        tor = t.exp(-((r - r0) / w) ** 2) * s ** 8
-        # compact support, as in the reference pgen: outside the torus surface the atmosphere is at rest and
-        # unmagnetised (v = 0, B = 0 exactly; ref: src/pgen/torus.cpp:246-262 atmosphere branch, and
-        # A_phi = max(rho/rho_max - 0.2, 0), torus.cpp:330-352) instead of Gaussian tails down to denormals
-        tor_v = t.where(tor > 1.0e-3, tor, t.zeros_like(tor))
-        tor_b = t.where(tor > 0.2, tor - 0.2, t.zeros_like(tor))
-        wig = 1.0 + seed_amp * t.sin(3.0 * X3 + 5.0 * X1) * t.cos(7.0 * th)
-        rho = 1.0e-5 * r ** -1.5 + tor * wig
-        u = kappa * rho ** gam / (gam - 1.0) + 1.0e-7 * r ** -2.5
-        prim = mesh.prim[n]
-        shape = prim.shape[1:]
-        prim[0] = rho.expand(shape)
-        prim[1] = 0.0
-        prim[2] = 0.0
-        prim[3] = (0.5 * tor_v * r ** -1.5).expand(shape)      # rotation about the axis (x3 = phi)
-        prim[4] = u.expand(shape)
-        if p.mhd:
-            b0 = 2.0e-3
-            prim[5] = (b0 * tor_b * t.cos(th) / r).expand(shape)
-            prim[6] = (b0 * tor_b * s / (r * r)).expand(shape)
-            prim[7] = 0.0
-        prim[mesh.nprim - 2] = ((gam - 1.0) * u).expand(shape)
-        prim[mesh.nprim - 1] = gam
+        s = mesh.geom_slot[n]
+        if s in done:
+            continue
+        done.add(s)
+        xm = (C.c_double * 3)(*mesh.bxmin[n])
+        dx = (C.c_double * 3)(*mesh.bdx[n])
+        _lib.check(L.pb_pgen_torus_table_host(gpar.ctypes.data_as(D), tpar.ctypes.data_as(D), C.byref(mesh.cfg), xm, dx,
+                                              mesh.geom_host[s].ctypes.data, out[s].ctypes.data), "pb_pgen_torus_table_host")
+    return out
 
 
-def p_get(p, key, default):
-    return float(getattr(p, "torus", {}).get(key, default)) if hasattr(p, "torus") else default
+def init_torus(mesh, drv, after_pgen=None):
+    """Fill the pack with the reference's torus initial state ("base" container + all OneCopy fields).
+    after_pgen(mesh): optional hook run between Mesh::Initialize and PostInitializationModifier (the test harness's
+    REF_DUMP_PERTURB acts there); it may modify mesh.prim and must leave the conserved variables to this function."""
+    L = _lib.lib()
+    t, p = mesh.torch, mesh.p
+    pk, cfg = C.byref(mesh.pack), C.byref(mesh.cfg)
+    s = drv._stream()
+    base = mesh.cons["base"]
+    I2 = C.c_int * 2
+    ent = (I2(0, mesh.ni - 1), I2(0, mesh.nj - 1), I2(0, mesh.nk - 1))
+    for f in (mesh.prim, mesh.temp, mesh.c2p_mu, mesh.fail, mesh.csig, mesh.fsig, base, mesh.cons["1"]):
+        f.zero_()  # Kokkos views start from zero (SURVEY.md A.17)
+    # ---- ProblemGenerator
+    table = t.from_numpy(torus_tables(mesh)).to(mesh.device)
+    _lib.check(L.pb_pgen_torus_fill(pk, cfg, table.data_ptr(), p.torus["u_jitter"], p.torus["seed"], s), "pb_pgen_torus_fill")
+    _lib.check(L.pb_pgen_torus_bfield(pk, cfg, s), "pb_pgen_torus_bfield")
+    _lib.check(L.pb_prim_to_cons(pk, cfg, base.data_ptr(), *ent, s), "pb_prim_to_cons")
+    _lib.check(L.pb_apply_floors(pk, cfg, base.data_ptr(), None, s), "pb_apply_floors")
+    # ---- CommunicateBoundaries (fill, no conversion) and FillDerived
+    drv.exchange(base)
+    _lib.check(L.pb_apply_bcs_ex(pk, cfg, base.data_ptr(), 1, s), "pb_apply_bcs_ex")
+    _lib.check(L.pb_cons_to_prim(pk, cfg, base.data_ptr(), *ent, s), "pb_cons_to_prim")
+    if after_pgen is not None:
+        after_pgen(mesh)
+        _lib.check(L.pb_prim_to_cons(pk, cfg, base.data_ptr(), *ent, s), "pb_prim_to_cons")
+    # ---- PostInitializationModifier: B normalisation (ref: torus.cpp:525-545,721-731)
+    fac = None
+    if p.mhd:
+        partial = t.zeros(3 * mesh.nblocks, dtype=t.float64, device=mesh.device)
+        out = (C.c_double * 3)()
+        _lib.check(L.pb_pgen_betas(pk, cfg, p.torus["rho_min_bnorm"], partial.data_ptr(), out, s), "pb_pgen_betas")
+        ext = list(out)
+        if drv.dist is not None:
+            v = t.tensor([-ext[0], ext[1], ext[2]], dtype=t.float64, device=mesh.device)
+            drv.dist.all_reduce(v, op=drv.dist.ReduceOp.MAX)
+            ext = [-float(v[0]), float(v[1]), float(v[2])]
+        small = 10.0 * np.finfo(np.float64).tiny
+        den = 0.5 * ext[1]
+        beta_pmax = ext[2] / (den + (small if den >= 0 else -small))  # robust::ratio
+        beta_norm = beta_pmax if p.torus["harm_beta_normalization"] else ext[0]
+        fac = math.sqrt(beta_norm / p.torus["target_beta"]) if p.torus["magnetized"] else 0.0
+        _lib.check(L.pb_scale_bfield(pk, cfg, fac, s), "pb_scale_bfield")
+        _lib.check(L.pb_prim_to_cons(pk, cfg, base.data_ptr(), *ent, s), "pb_prim_to_cons")
+    mesh.invalidate_flags()
+    drv.has_face_speeds = False  # ref: fluid.cpp:911,940 — the first EstimateTimestep uses cell speeds only
+    return fac
+
+
+def hash_perturbation(mesh, amp):
+    """after_pgen hook reproducing oracle/ref_harness/ref_dump.cpp's REF_DUMP_PERTURB on the device: rho, u, v^3 of every
+    zone times 1 + amp (h - 0.5), h an integer hash of the zone's global index (periodic in x3)"""
+    t = mesh.torch
+    dev = mesh.device
+
+    def hash_unit(gi, gj, gk, salt):
+        def mul(a, c):  # 64-bit wrap-around product; torch has no uint64 arithmetic, int64 wraps identically
+            return a * t.tensor(c if c < (1 << 63) else c - (1 << 64), dtype=t.int64, device=dev)
+        x = mul(gi + 4096, 73856093) ^ mul(gj + 4096, 19349663) ^ mul(gk + 4096, 83492791) ^ int(salt * 2654435761)
+        x = x ^ ((x >> 15) & ((1 << 49) - 1))   # logical shift of the two's-complement pattern
+        x = mul(x, 0x2c1b3c6d)
+        x = x ^ ((x >> 12) & ((1 << 52) - 1))
+        return (x & 1023).to(t.float64) / 1024.0
+
+    def hook(mesh):
+        ng, ndim = mesh.ng, mesh.ndim
+        for n in range(mesh.nblocks):
+            org = []
+            for d in range(3):
+                if d >= ndim:
+                    org.append(0)
+                    continue
+                xf = mesh.bxmin[n, d] + ng * mesh.bdx[n, d]
+                org.append(int(round((xf - mesh.mesh_xmin[d]) / mesh.bdx[n, d])))
+            gi = (t.arange(mesh.ni, dtype=t.int64, device=dev) + (org[0] - ng)).view(1, 1, -1)
+            gj = ((t.arange(mesh.nj, dtype=t.int64, device=dev) + (org[1] - ng)) if ndim >= 2 else t.zeros(1, dtype=t.int64, device=dev)).view(1, -1, 1)
+            if ndim >= 3:
+                nx3 = mesh.p.mesh_nx[2]
+                gk = t.remainder(t.arange(mesh.nk, dtype=t.int64, device=dev) + (org[2] - ng), nx3).view(-1, 1, 1)
+            else:
+                gk = t.zeros(1, dtype=t.int64, device=dev).view(1, 1, 1)
+            gi, gj, gk = t.broadcast_tensors(gi, gj, gk)
+            prim = mesh.prim[n]
+            prim[0] *= 1.0 + amp * (hash_unit(gi, gj, gk, 1) - 0.5)
+            prim[4] *= 1.0 + amp * (hash_unit(gi, gj, gk, 2) - 0.5)
+            prim[3] *= 1.0 + amp * (hash_unit(gi, gj, gk, 3) - 0.5)
+    return hook
