@@ -7,7 +7,9 @@
 A step is one RK2 cycle (two stages + the dt estimate) of the weak-scaling torus of
 BASELINE.json configs[4]: FMKS Kerr-Schild a=0.9375, ideal gas, weno5 + llf, MHD, floors /
 ceilings / c2p fixup / flux fixup on, bc_vars = primitive, 256^3 zones per GPU in 32^3 MeshBlocks.
-Initial data is synthetic (phoebus_b200/pgen.py), generated in HBM.
+Initial data: the reference's own Fishbone-Moncrief torus (phoebus_b200/pgen.py: init_torus — atmosphere at the floors,
+vector-potential B normalised to beta = 100, 5 % energy jitter), generated through the C ABI; the reference arm runs the
+same deck on a smaller mesh.
 Prints ONE JSON line (contract in the task statement).
 """
 import argparse
@@ -26,10 +28,21 @@ STRONG_MESH = (256, 128, 128)  # inputs/torus.pin in 3-D: 12
 # contract-minimum words per zone-stage, 3-D MHD (Nc=8, Nr=10, g=1.953)
 A_TASK_BYTES_PER_ZONE_CYCLE = 2368.0
 G1_WORDS_PER_ZONE_STAGE = 37.0  # CalculateFluxes: R 10 prims, W 3x8 fluxes, W 3 face speeds
-# from the committed ncu captures of this same command (profiles/r01_ncu_full_bench_256cube.md): dram bytes per launch at
-# 256^3 zones per GPU, and the FP64 pipe utilisation (sm__inst_executed_pipe_fp64 pct of peak sustained active)
-NCU_DRAM_BYTES_PER_LAUNCH = {"recon_kernel": 6.08e9, "flux_kernel": None}
-NCU_FP64_PIPE_PCT = {"recon_kernel": 81.9, "flux_kernel": 50.0}
+DT_INIT_FACT = 1.0e-2  # both arms: first step = 1e-2 x the CFL step, doubling per cycle (the deck's 1e-6 needs 20 cycles to get there)
+
+
+def ncu_kernel_metrics(kernel):
+    """dram bytes per launch and FP64-pipe utilisation of `kernel` from the committed summary of the ncu --set full capture
+    of this same command (profiles/ncu_kernel_metrics.json, written by scripts/ncu_to_json.py); None when there is none"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_kernel_metrics.json")) as f:
+            m = json.load(f)
+        k = m["kernels"].get(kernel)
+        if k:
+            return dict(k, source=m.get("source"))
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
 
 
 def deck_text(name="torus3d"):
@@ -84,6 +97,7 @@ def build_mesh(args, rank, world, device):
     nx = tuple(args.mesh) if args.mesh else (STRONG_MESH if args.strong else WEAK_MESH[world])
     ov = ["parthenon/mesh/nx%d=%d" % (d + 1, nx[d]) for d in range(3)]
     ov += ["parthenon/meshblock/nx%d=%d" % (d + 1, args.block) for d in range(3)]
+    ov += ["parthenon/time/dt_init_fact=%r" % DT_INIT_FACT]
     pin = ParameterInput(deck_text(), ov)
     torus_problem_modifier(pin)
     fp = FluidParams(pin)
@@ -91,23 +105,12 @@ def build_mesh(args, rank, world, device):
 
 
 def init_state(mesh, drv):
-    """pgen -> PrimitiveToConserved -> FillDerived (c2p) + fixup + floors, as ParthenonInitPackagesAndMesh does"""
-    import ctypes as C
-    from phoebus_b200 import _lib
-    from phoebus_b200.pgen import synthetic_torus
-    L = _lib.lib()
-    synthetic_torus(mesh)
-    pk, cfg = C.byref(mesh.pack), C.byref(mesh.cfg)
-    s = drv._stream()
-    I2 = C.c_int * 2
-    ib, jb, kb = I2(0, mesh.ni - 1), I2(0, mesh.nj - 1), I2(0, mesh.nk - 1)
-    base = mesh.cons["base"]
-    _lib.check(L.pb_prim_to_cons(pk, cfg, base.data_ptr(), ib, jb, kb, s), "pb_prim_to_cons")
-    drv.exchange(base)
-    mesh.invalidate_flags()
+    """the reference's start-up sequence for `problem = torus` (Mesh::Initialize + PostInitializationModifier)"""
+    from phoebus_b200.pgen import init_torus
+    fac = init_torus(mesh, drv)
     drv.ensure_flags()
-    _lib.check(L.pb_rk_stage_post(pk, cfg, base.data_ptr(), C.c_void_p(mesh.counters.data_ptr()), s), "init c2p")
     mesh.counters.zero_()
+    return fac
 
 
 def e2e_cycles(torch, drv, host_t, dev_t, steps, dt, pipelined=True):
@@ -186,10 +189,11 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # time-step control as the reference's driver: first step = dt_init_fact x the CFL proposal, then min(2 dt, CFL)
     dt = drv.estimate_dt()
     drv.dt = dt
     drv.first_step = False
-    dt *= 0.1  # gentle start for the synthetic (non-equilibrium) state; grows 2x per cycle to the CFL value
+    dt *= fp.dt_init_fact
     for _ in range(args.warmup):
         drv.step(dt)
         dt = drv.propose_dt(dt)
@@ -277,20 +281,23 @@ def run_ours(args):
         kname = "flux_kernel<DIR,weno5z,mhd> (fused reconstruction + Riemann, one launch per direction)"
     avg_ms = k_ms / nlaunch
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    ncu = ncu_kernel_metrics(kname.split("<")[0]) or {}
     out = {
         "metric": "zone-cycles/s", "value": value, "unit": "zone-cycles/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (Fishbone-Moncrief torus generated in HBM)",
         "config": {"workload": "3-D FMKS torus GRMHD, strong scaling, fixed 256x128x128 mesh (BASELINE.json configs[3])" if args.strong
                    else "3-D FMKS torus GRMHD, weak scaling (BASELINE.json configs[4])", "mesh": list(nx),
                    "meshblock": [args.block] * 3, "zones_per_gpu": zones_rank, "blocks_per_gpu": mesh.nblocks,
                    "recon": fp.recon, "riemann": fp.riemann, "integrator": "rk2", "geometry": "fmks a=0.9375 (host-tabulated, axisymmetric)",
+                   "initial_data": "Fishbone-Moncrief torus rin=6 rmax=12, atmosphere at the floors, beta=100, u_jitter=0.05 (ref: src/pgen/torus.cpp)",
+                   "dt_init_fact": fp.dt_init_fact,
                    "parallelism": "meshblock bricks %s" % "x".join(map(str, mesh.rgrid)),
                    "l2": "working set %.1f GB per GPU >> 126 MB L2" % (mesh.bytes_allocated() / 1e9)},
         "roofline": {"bound": "hbm", "kernel": kname, "co_bound": "fp64 pipe (no FMA contraction: bit parity with the reference)",
-                     "fp64_pipe_pct_ncu": NCU_FP64_PIPE_PCT.get(kname.split("<")[0]), "traffic_source": "profiles/r01_ncu_full_bench_256cube.md",
+                     "fp64_pipe_pct_ncu": ncu.get("fp64_pipe_pct"), "traffic_source": ncu.get("source"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(kname.split("<")[0]), "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic": ncu.get("dram_bytes_per_launch"), "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                      "step_frac_of_hbm_roofline": value / world * A_TASK_BYTES_PER_ZONE_CYCLE / (peak * 1e9)},
         "breakdown_ms_per_step": {k: v[1] / args.steps for k, v in sorted(tsum.items())},
         "gpu_launches": launches,
@@ -320,7 +327,8 @@ def run_reference_binary(nx, block, ncycles, threads):
     exe, deck = ref_binary()
     ov = ["parthenon/mesh/nx%d=%d" % (d + 1, nx[d]) for d in range(3)]
     ov += ["parthenon/meshblock/nx%d=%d" % (d + 1, block) for d in range(3)]
-    ov += ["parthenon/time/nlim=%d" % (ncycles + 2), "parthenon/time/perf_cycle_offset=2", "torus/seed=7"]
+    ov += ["parthenon/time/nlim=%d" % (ncycles + 2), "parthenon/time/perf_cycle_offset=2", "torus/seed=7",
+           "parthenon/time/dt_init_fact=%r" % DT_INIT_FACT]
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="threads")
     import tempfile
     with tempfile.TemporaryDirectory() as tmp:
@@ -439,7 +447,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "zone-cycles/s", "value": cb["value"], "unit": "zone-cycles/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * nx[0] * nx[1] * nx[2] / cb["value"], "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic (Fishbone-Moncrief torus generated in HBM)",
            "config": {"workload": "3-D FMKS torus GRMHD (bounded CPU sample of BASELINE.json configs[4])", "mesh": list(nx),
                       "meshblock": [32] * 3},
            "cpu_baseline": cb,

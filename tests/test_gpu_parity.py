@@ -189,8 +189,7 @@ def test_tasks_match_oracle(name):
     compare("halo")
     _lib.check(L.pb_apply_bcs(pk, cfg, one.data_ptr(), s))
     for n, b in blocks:
-        for _ in range(2):
-            OL.orc_apply_bcs(C.byref(b.cfg), b.geom, b.cons["1"], b.prim, b.temp, b.c2p_mu, b.fail, b.csig)
+        OL.orc_apply_bcs(C.byref(b.cfg), b.geom, b.cons["1"], b.prim, b.temp, b.c2p_mu, b.fail, b.csig)
     compare("bcs")
     I2 = C.c_int * 2
     ib, jb, kb = I2(0, mesh.ni - 1), I2(0, mesh.nj - 1), I2(0, mesh.nk - 1)
@@ -570,3 +569,93 @@ def test_e2e_duplex_pipeline_matches_naive_loop():
         results.append([h.numpy().copy() for h in host_t])
     for a, b in zip(*results):
         assert np.array_equal(a, b, equal_nan=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# problem generator + the benchmarked configuration
+def _init_ref(g, gid, shape):
+    get = getter(g, "init")
+    return dict(prim=fd.stack(get, gid, "base", fd.PRIM_FIELDS, shape), temp=get(gid, "base", "temperature").reshape(shape),
+                c2p_mu=get(gid, "base", "c2p_mu").reshape(shape), fail=get(gid, "base", "fail").reshape(shape),
+                csig=get(gid, "base", "cell_signal_speed").reshape((-1,) + shape),
+                cons=fd.stack(get, gid, "base", fd.CONS_FIELDS, shape))
+
+
+@pytest.mark.parametrize("name", ["torus2d", "torus3d", "torus2d_polar"])
+def test_torus_pgen_matches_reference_init(name):
+    """phoebus_b200.pgen.init_torus (host table + device kernels + the reference's start-up sequence through the C ABI)
+    reproduces every field of the reference's state before its first cycle, ghosts included, and its first time step"""
+    from phoebus_b200 import pgen
+    from phoebus_b200.driver import FluidDriver
+    g, p = load_case(name)
+    mesh, fp = product_mesh(g, device=_dev())
+    drv = FluidDriver(mesh)
+    amp = float(g.meta.get("env", {}).get("REF_DUMP_PERTURB", 0) or 0)
+    pgen.init_torus(mesh, drv, after_pgen=pgen.hash_perturbation(mesh, amp) if amp else None)
+    mesh.torch.cuda.synchronize()
+    man = g.manifest("init")
+    for mb in man["blocks"]:
+        n = mesh.local_index[block_lx(mesh, man, mb, mesh.ndim, mesh.ng, mesh.nx)]
+        ref = _init_ref(g, mb["gid"], mesh.shape)
+        for k in FIELDS:
+            mine = _np(getattr(mesh, k)[n]).reshape(ref[k].shape)
+            assert np.array_equal(mine, ref[k], equal_nan=True), (name, mb["gid"], k, fd.relerr(mine, ref[k]))
+        assert np.array_equal(_np(mesh.cons["base"][n]), ref["cons"], equal_nan=True), (name, mb["gid"], "cons")
+    # first cycle's dt: cfl * min dt (cell speeds only) * dt_init_fact (phoebus_driver.cpp:121-132)
+    first = g.manifest(stage_tags(g)[0])
+    assert drv.estimate_dt() * fp.dt_init_fact == first["dt"]
+
+
+def test_hashed_fixture_with_32cube_meshblocks():
+    """The production block shape: 3-D FMKS torus, 2x2x2 MeshBlocks of 32^3, ng = 4 (Shell enumeration, packed flag scans
+    and halo plans at the sizes the benchmark uses), two RK2 cycles. The committed fixture holds one hash per array of the
+    unmodified reference's dumps (oracle/refdump.py: array_hash); the initial state is rebuilt with the product's own
+    torus pgen plus the harness's hash perturbation and must hash to the reference's init dump as well."""
+    from oracle import refdump
+    from phoebus_b200 import pgen
+    from phoebus_b200.driver import FluidDriver
+    from phoebus_b200.mesh import MeshPack
+    from phoebus_b200.params import FluidParams, ParameterInput
+    h = refdump.Hashed(os.path.join(ROOT_DIR, "tests", "golden", "torus3d_b32.json"))
+    man = h.manifest("init")
+    pin = ParameterInput.from_blocks(h.meta["deck_blocks"])
+    for k, v in man["mesh"].items():
+        pin.blocks.setdefault("parthenon/mesh", {})[k] = repr(float(v))
+    pin.blocks.setdefault("geometry", {})["kind"] = "fmks"
+    fp = FluidParams(pin)
+    mesh = MeshPack(fp, device=_dev())
+    assert mesh.nblocks == 8 and mesh.nx == (32, 32, 32)
+    order = {}
+    for mb in man["blocks"]:
+        n = mesh.local_index[block_lx(mesh, man, mb, mesh.ndim, mesh.ng, mesh.nx)]
+        assert np.array_equal(mesh.bxmin[n], mb["xmin"]) and np.array_equal(mesh.bdx[n], mb["dx"])
+        order[mb["gid"]] = n
+    drv = FluidDriver(mesh)
+    pgen.init_torus(mesh, drv, after_pgen=pgen.hash_perturbation(mesh, float(h.meta["env"]["REF_DUMP_PERTURB"])))
+    drv.estimate_dt()
+
+    def check(tag, sc1):
+        mesh.torch.cuda.synchronize()
+        for gid, n in order.items():
+            P = _np(mesh.prim[n])
+            arrs = {"p.density": P[0:1], "p.velocity": P[1:4], "p.energy": P[4:5], "p.bfield": P[5:8], "pressure": P[8:9],
+                    "gamma1": P[9:10], "temperature": _np(mesh.temp[n]), "c2p_mu": _np(mesh.c2p_mu[n]), "fail": _np(mesh.fail[n]),
+                    "cell_signal_speed": _np(mesh.csig[n])}
+            for nm, a in arrs.items():
+                assert refdump.array_hash(a) == h.hash(tag, gid, "base", nm), (tag, gid, nm)
+            U = _np(mesh.cons[sc1][n])
+            for nm, a in {"c.density": U[0:1], "c.momentum": U[1:4], "c.energy": U[4:5], "c.bfield": U[5:8]}.items():
+                assert refdump.array_hash(a) == h.hash(tag, gid, sc1, nm), (tag, gid, sc1, nm)
+    check("init", "base")
+    for tag in h.meta["tags"][1:]:
+        m = h.manifest(tag)
+        drv.stage(m["stage"], m["dt"])
+        check(tag, m["sc1"])
+    # the same two cycles sequenced as the multi-GPU path does (pre / halo + early con2prim / post2) give the same hashes
+    pgen.init_torus(mesh, drv, after_pgen=pgen.hash_perturbation(mesh, float(h.meta["env"]["REF_DUMP_PERTURB"])))
+    drv.estimate_dt()
+    drv.force_split = True
+    for tag in h.meta["tags"][1:]:
+        m = h.manifest(tag)
+        drv.stage(m["stage"], m["dt"])
+        check(tag, m["sc1"])
