@@ -100,8 +100,10 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
       const Real *p = v + (size_t)n * L.ncell;
       Real *d = s_in + n * plane_in + in0;
       cp_async8(d + 2 * in_st, p);
-      if (sI < 2) cp_async8(d, p - 2 * st);
-      if (sI >= NS - 2) cp_async8(d + 4 * in_st, p + 2 * st);
+      // only the cells the scheme reads: none beyond the tile for constant, one for linear, two for weno5 / mp5
+      // (with nghost = 2 and linear reconstruction the second one would lie outside the block)
+      if (sI < 2 && (RECON >= 2 || (RECON == 1 && sI == 1))) cp_async8(d, p - 2 * st);
+      if (sI >= NS - 2 && (RECON >= 2 || (RECON == 1 && sI == NS - 2))) cp_async8(d + 4 * in_st, p + 2 * st);
     }
   }
   cp_async_commit();

@@ -52,6 +52,16 @@ PB_DEV bool cell_of_thread(const Box &r, int nblocks, int &b, int &k, int &j, in
 #define PB_RECON_T 256
 #endif
 
+// the cells the scheme reads and no others: with nghost = 2 and linear reconstruction (the reference's default deck
+// values) the cells at distance 2 of the first / last reconstructed cell lie outside the block
+template <int RECON> PB_DEV void load_stencil(const Real *p, int st, Real q[5]) {
+  q[2] = __ldg(p);
+  q[1] = RECON >= 1 ? __ldg(p - st) : q[2];
+  q[3] = RECON >= 1 ? __ldg(p + st) : q[2];
+  q[0] = RECON >= 2 ? __ldg(p - 2 * st) : q[2];
+  q[4] = RECON >= 2 ? __ldg(p + 2 * st) : q[2];
+}
+
 template <int DIR, int RECON, int NP>
 __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const Real *__restrict__ prim, Real *__restrict__ ql,
                                                                    Real *__restrict__ qr, const pb_cfg_t cfg, const Box reg,
@@ -69,7 +79,9 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
   for (int n = 0; n < NP; ++n) {
     const Real *p = v + (size_t)n * L.ncell;
     Real a, c;
-    recon5z<RECON>(af, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), a, c);
+    Real q[5];
+    load_stencil<RECON>(p, st, q);
+    recon5z<RECON>(af, q[0], q[1], q[2], q[3], q[4], a, c);
     l[(size_t)n * L.ncell] = a;
     r[(size_t)n * L.ncell] = c;
   }
@@ -79,7 +91,9 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
     for (int n = 0; n < NP; ++n) {
       const Real *p = v + (size_t)n * L.ncell;
       Real a, c;
-      recon5z<RECON>(ax, __ldg(p - 2 * st), __ldg(p - st), __ldg(p), __ldg(p + st), __ldg(p + 2 * st), a, c);
+      Real q[5];
+      load_stencil<RECON>(p, st, q);
+      recon5z<RECON>(ax, q[0], q[1], q[2], q[3], q[4], a, c);
       l[(size_t)n * L.ncell] = a;
       r[(size_t)n * L.ncell] = c;
     }
