@@ -179,7 +179,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus, "--gpus must equal WORLD_SIZE"
     mesh, fp, nx = build_mesh(args, rank, world, device)
-    drv = FluidDriver(mesh, dist if world > 1 else None)
+    drv = FluidDriver(mesh, dist if world > 1 else None, halo=args.halo, use_graphs=args.graphs)
     init_state(mesh, drv)
     zones_total = nx[0] * nx[1] * nx[2]
 
@@ -202,7 +202,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    drv.enable_profile(True)
+    drv.enable_profile(not args.graphs)  # the per-task events cannot be recorded inside a graph replay
+    drv.L.pb_c2p_stats(1, None)
     launches0 = drv.launches
     redo0 = drv.L.pb_arith_redo_count()
     mesh.counters.zero_()
@@ -223,6 +224,10 @@ def run_ours(args):
     tsum = drv.timer_summary()
     drv.enable_profile(False)
     redo = float(drv.L.pb_arith_redo_count() - redo0)
+    import ctypes as C
+    c2p_stats = (C.c_ulonglong * 36)()
+    drv.L.pb_c2p_stats(0, c2p_stats)
+    c2p_stats = [int(x) for x in c2p_stats]
     counters = mesh.counters.clone()
     nfail = (mesh.fail == 0).sum()
     finite = torch.isfinite(mesh.cons["base"]).all() & torch.isfinite(mesh.prim).all()
@@ -293,6 +298,8 @@ def run_ours(args):
                    "initial_data": "Fishbone-Moncrief torus rin=6 rmax=12, atmosphere at the floors, beta=100, u_jitter=0.05 (ref: src/pgen/torus.cpp)",
                    "dt_init_fact": fp.dt_init_fact,
                    "parallelism": "meshblock bricks %s" % "x".join(map(str, mesh.rgrid)),
+                   "halo_transport": ("ncclSend/ncclRecv inside the C ABI" if args.halo == "nccl" else "torch.distributed") if world > 1 else None,
+                   "cuda_graphs": bool(args.graphs),
                    "l2": "working set %.1f GB per GPU >> 126 MB L2" % (mesh.bytes_allocated() / 1e9)},
         "roofline": {"bound": "hbm", "kernel": kname, "co_bound": "fp64 pipe (no FMA contraction: bit parity with the reference)",
                      "fp64_pipe_pct_ncu": ncu.get("fp64_pipe_pct"), "traffic_source": ncu.get("source"),
@@ -303,7 +310,12 @@ def run_ours(args):
         "gpu_launches": launches,
         "zone_stats": {"floors": int(stats[0]), "ceilings": int(stats[1]), "floor_c2p_fail": int(stats[2]),
                        "failed_zones_now": int(stats[3]), "nonfinite": int(stats[4]),
-                       "arith_redo_items": int(stats[5])},
+                       "arith_redo_items": int(stats[5]),
+                       # rank 0's con2prim statistics over the timed cycles (the reference's CON2PRIM_STATISTICS, con2prim_statistics.hpp)
+                       "c2p_iteration_histogram": c2p_stats[:32], "c2p_zones_solved": c2p_stats[35],
+                       "c2p_used_floor_or_ceiling": c2p_stats[32], "c2p_failed": c2p_stats[33],
+                       "c2p_parked_by_warp_vote": c2p_stats[34],
+                       "c2p_mean_iterations": (sum(i * n for i, n in enumerate(c2p_stats[:32])) / max(1, sum(c2p_stats[:32])))},
         "clocks": sampler.summary(),
     }
     if e2e:
@@ -466,6 +478,9 @@ def main():
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: the fixed 256x128x128 torus of inputs/torus.pin (BASELINE.json configs[3]) on N GPUs")
     ap.add_argument("--block", type=int, default=32)
+    ap.add_argument("--graphs", action="store_true", help="replay every RK stage as one CUDA graph (no per-task breakdown then)")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "torch"],
+                    help="inter-GPU ghost transport: NCCL inside the C ABI (default) or torch.distributed")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-port", action="store_true", help="cpu baseline: use the oracle port even if oracle/_ref exists")

@@ -220,6 +220,47 @@ int pb_halo_pack(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons,
                  int nseg, double *buf, void *stream);
 int pb_halo_unpack(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *plan,
                    int nseg, const double *buf, void *stream);
+/* ---- inter-GPU ghost exchange over NCCL (ref: parthenon SendBoundBufs / ReceiveBoundBufs / SetBounds over MPI,
+ * external/parthenon/src/bvals/comms/boundary_communication.cpp:49-346). NCCL is resolved at run time (dlopen of
+ * libnccl.so.2); none of this is needed on one GPU. One process per GPU: rank 0 creates the id, every rank receives it
+ * out of band (MPI_Bcast, torch.distributed broadcast, a file ...) and calls pb_comm_init. */
+int pb_comm_unique_id(char out[128]);
+int pb_comm_init(void **comm_out, int rank, int world, const char id[128]);
+int pb_comm_destroy(void *comm);
+/* All segments of all peers in ONE send and ONE receive buffer (device); NCCL moves the per-peer slices. */
+typedef struct pb_halo_plan {
+  const int *send_plan; /* device [nsend][10], rows as pb_halo_pack */
+  int nsend;
+  const int *recv_plan; /* device [nrecv][10] */
+  int nrecv;
+  double *send_buf, *recv_buf; /* device */
+  int npeers;
+  const int *peer;                         /* host [npeers] rank of each peer */
+  const long long *send_off, *send_cnt;    /* host [npeers] slice of send_buf, in doubles */
+  const long long *recv_off, *recv_cnt;    /* host [npeers] slice of recv_buf */
+} pb_halo_plan_t;
+/* begin: pack on `stream`, then one grouped ncclSend / ncclRecv per peer on the communicator's own stream. Between begin and
+ * end the caller issues the work that hides the transfer on `stream` (pb_halo_exchange_local, pb_rk_stage_post_early).
+ * end: `stream` waits for the arrival and unpacks into the ghost zones. */
+int pb_halo_exchange_begin(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, const pb_halo_plan_t *plan,
+                           void *comm, void *stream);
+int pb_halo_exchange_end(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const pb_halo_plan_t *plan, void *comm,
+                         void *stream);
+/* min over ranks of n device doubles, in place on `stream` (the dt reduction, ref: parthenon driver.cpp:237) */
+int pb_comm_allreduce_min(void *comm, double *value_dev, int n, void *stream);
+/* Time-step control on the device (ref: parthenon driver.cpp:216-240): dt <- min(2 dt, cfl * est), est = the value
+ * pb_estimate_dt reduced into; no host round trip. */
+int pb_dt_control(const double *est_dev, double cfl, double *dt_dev, void *stream);
+/* One RK stage captured as a CUDA graph (launch-latency bound packs: strong scaling): the launches of pb_rk_stage
+ * (comm == NULL) or of pb_rk_stage_pre / exchange with the interior con2prim under the transfer / pb_rk_stage_post2
+ * (comm != NULL), with dt read from device memory at run time. Call after at least one ordinary stage on the same pack
+ * (work spaces are sized then); per-task profiling must be off. */
+int pb_stage_graph_create(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc0, double *base, double *sc1, double beta,
+                          const double *dt_dev, unsigned long long *counters, const pb_halo_plan_t *plan, void *comm,
+                          void *stream, void **graph_out);
+int pb_stage_graph_launch(void *graph, void *stream);
+int pb_stage_graph_destroy(void *graph);
+
 /* Physical boundary ghost fill + Boundaries::ConvertBoundaryConditions,
  * ref: src/phoebus_boundaries/phoebus_boundaries.cpp:44-448 */
 int pb_apply_bcs(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream);
@@ -293,13 +334,19 @@ int pb_profile_read(double ms[PB_NTASK], int calls[PB_NTASK]);
 
 /* Run-time options of the library (initial values from the environment variables in parentheses):
  *   "flux_split" 1|0  (PB_FLUX_MODE=split|fused)  two-launch flux path when the pack has recon_lr, else the fused kernel
- *   "c2p_arith"  2|0|1 (PB_C2P_ARITH=queue|exact|inline) con2prim arithmetic: ArithFast + redo queue, the compiler's
- *                divide / sqrt, ArithFast with an inline exact re-solve. All settings produce identical bits. */
+ *   "c2p_arith"  3|2|0|1 (PB_C2P_ARITH=split|queue|exact|inline) con2prim: root find and unwrap as separate launches with
+ *                warp-level parking of slowly converging zones (default); one kernel with ArithFast + redo queue; the
+ *                compiler's divide / sqrt; ArithFast with an inline exact re-solve. All settings produce identical bits. */
 int pb_set_option(const char *key, int value);
 int pb_get_option(const char *key);
 /* Faces / zones that the fast arithmetic rejected and riemann_redo_kernel / c2p_redo_kernel recomputed with the compiler's divide / sqrt,
  * accumulated since the library was loaded (synchronises the device). */
 unsigned long long pb_arith_redo_count(void);
+/* Con2prim statistics (the reference's CON2PRIM_STATISTICS histogram, ref: src/fluid/con2prim_statistics.hpp:22-41): enable != 0
+ * starts counting (zeroing the counters), 0 stops; out_host (may be NULL) receives the 36 counters accumulated so far:
+ * [0..31] regula-falsi iterations per solve (31 = 31 or more), [32] solves that used a floor / ceiling, [33] failed zones,
+ * [34] zones parked by the warp vote, [35] zones unwrapped. Counted by the split con2prim path only. Synchronises the device. */
+int pb_c2p_stats(int enable, unsigned long long out_host[36]);
 /* Same idea one level up: riemann.hpp's prim_to_flux (face state -> U, F, v+-) evaluated with the
  * deferred-branch arithmetic and with the compiler's, on n synthetic MHD face states (flat != 0:
  * Minkowski metric; else a random metric). counts_dev[0] = states whose outputs differ in any bit,

@@ -41,6 +41,13 @@ class PbCfg(C.Structure):
     ]
 
 
+class PbHaloPlan(C.Structure):
+    _fields_ = [("send_plan", C.c_void_p), ("nsend", C.c_int), ("recv_plan", C.c_void_p), ("nrecv", C.c_int),
+                ("send_buf", C.c_void_p), ("recv_buf", C.c_void_p), ("npeers", C.c_int), ("peer", C.POINTER(C.c_int)),
+                ("send_off", C.POINTER(C.c_longlong)), ("send_cnt", C.POINTER(C.c_longlong)),
+                ("recv_off", C.POINTER(C.c_longlong)), ("recv_cnt", C.POINTER(C.c_longlong))]
+
+
 class PbPack(C.Structure):
     _fields_ = [("nblocks", C.c_int), ("blocks", C.c_void_p), ("geom", C.c_void_p), ("floor_tab", C.c_void_p),
                 ("prim", C.c_void_p), ("temp", C.c_void_p), ("c2p_mu", C.c_void_p), ("fail", C.c_void_p),
@@ -78,6 +85,16 @@ SYMBOLS = {
     "pb_halo_nvar": (C.c_int, [_CFG]),
     "pb_halo_pack": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P, _P]),
     "pb_halo_unpack": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P, _P]),
+    "pb_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "pb_comm_init": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_char_p]),
+    "pb_comm_destroy": (C.c_int, [_P]),
+    "pb_halo_exchange_begin": (C.c_int, [_PACK, _CFG, _P, C.POINTER(PbHaloPlan), _P, _P]),
+    "pb_halo_exchange_end": (C.c_int, [_PACK, _CFG, _P, C.POINTER(PbHaloPlan), _P, _P]),
+    "pb_comm_allreduce_min": (C.c_int, [_P, _P, C.c_int, _P]),
+    "pb_dt_control": (C.c_int, [_P, C.c_double, _P, _P]),
+    "pb_stage_graph_create": (C.c_int, [_PACK, _CFG, _P, _P, _P, C.c_double, _P, _P, C.POINTER(PbHaloPlan), _P, _P, C.POINTER(C.c_void_p)]),
+    "pb_stage_graph_launch": (C.c_int, [_P, _P]),
+    "pb_stage_graph_destroy": (C.c_int, [_P]),
     "pb_apply_bcs": (C.c_int, [_PACK, _CFG, _P, _P]),
     "pb_apply_bcs_ex": (C.c_int, [_PACK, _CFG, _P, C.c_int, _P]),
     "pb_pgen_torus_table_host": (C.c_int, [_D3, _D3, _CFG, _D3, _D3, _P, _P]),
@@ -93,6 +110,7 @@ SYMBOLS = {
     "pb_profile_read": (C.c_int, [_P, _P]),
     "pb_selftest_arith": (C.c_int, [C.c_longlong, C.c_ulonglong, C.c_int, _P, _P]),
     "pb_arith_redo_count": (C.c_ulonglong, []),
+    "pb_c2p_stats": (C.c_int, [C.c_int, _P]),
     "pb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "pb_get_option": (C.c_int, [C.c_char_p]),
     "pb_selftest_riemann": (C.c_int, [C.c_longlong, C.c_ulonglong, _CFG, C.c_int, _P, _P, _P]),

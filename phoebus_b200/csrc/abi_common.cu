@@ -56,8 +56,16 @@ static int g_flux_split = [] {
 }();
 static int g_c2p_arith = [] {
   const char *e = getenv("PB_C2P_ARITH");
-  return (e && e[0] == 'e') ? 0 : ((e && e[0] == 'i') ? 1 : 2);
+  return (e && e[0] == 'e') ? 0 : ((e && e[0] == 'i') ? 1 : ((e && e[0] == 'q') ? 2 : 3));
 }();
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    return v;
+  }();
+  return n;
+}
 bool flux_split_enabled() { return g_flux_split != 0; }
 int c2p_arith_mode() { return g_c2p_arith; }
 int zone_threads() {
@@ -165,7 +173,7 @@ void prof_end(int id, cudaStream_t s) {
 
 extern "C" int pb_set_option(const char *key, int value) {
   if (key && !strcmp(key, "flux_split")) g_flux_split = value != 0;
-  else if (key && !strcmp(key, "c2p_arith") && value >= 0 && value <= 2) g_c2p_arith = value;
+  else if (key && !strcmp(key, "c2p_arith") && value >= 0 && value <= 3) g_c2p_arith = value;
   else return set_error(PB_EINVAL, "pb_set_option: unknown key or value");
   return PB_OK;
 }

@@ -18,7 +18,8 @@ int check_args(const pb_pack_t *pack, const pb_cfg_t *cfg);
 int flux_threads_target();
 int zone_threads();
 bool flux_split_enabled(); // option flux_split / PB_FLUX_MODE=fused|split (default split when the pack carries ql/qr scratch)
-int c2p_arith_mode();      // option c2p_arith / PB_C2P_ARITH: 0 exact, 1 inline, 2 queue (default)
+int c2p_arith_mode();      // option c2p_arith / PB_C2P_ARITH: 0 exact, 1 inline, 2 queue, 3 split (default)
+int sm_count();            // SMs of the current device (grid sizing of the persistent / grid-stride launches)
 
 // Device queue of work items (linear thread indices) that the deferred-branch arithmetic (ArithFast, pb_device.cuh)
 // rejected; a *_redo_kernel recomputes exactly those items with the compiler's divide / sqrt right after, on the same

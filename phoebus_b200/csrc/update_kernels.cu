@@ -313,7 +313,8 @@ template <bool MHD> __global__ void source_kernel(const pb_pack_t pack, const pb
 // ref: src/phoebus_driver.cpp:560-576, external/parthenon/src/interface/update.hpp:71-136
 template <bool MHD>
 __global__ void __launch_bounds__(128, 5) update_fused_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *u0, const Real *ubase,
-                                    Real beta, Real bdt, Real *uout, Real *dudt_out, Real *gsrc_out) {
+                                    Real beta, Real bdt, Real *uout, Real *dudt_out, Real *gsrc_out, const Real *dt_dev) {
+  if (dt_dev) bdt = beta * __ldg(dt_dev); // graph replay: the step size lives in device memory
   constexpr int NCn = NC<MHD>::ncons, NP = NC<MHD>::nprim;
   const Lay L(cfg);
   int b, k, j, i;
@@ -344,7 +345,9 @@ __global__ void __launch_bounds__(128, 5) update_fused_kernel(const pb_pack_t pa
 // launch): a pure streaming kernel (24 flux + 4 source + 16 cons words in, 8 out per zone), few registers.
 template <bool MHD>
 __global__ void __launch_bounds__(256, 4) update_stream_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *u0, const Real *ubase,
-                                                               Real beta, Real bdt, Real *uout, const Real *gsrc, Real *dudt_out) {
+                                                               Real beta, Real bdt, Real *uout, const Real *gsrc, Real *dudt_out,
+                                                               const Real *dt_dev) {
+  if (dt_dev) bdt = beta * __ldg(dt_dev); // graph replay: the step size lives in device memory
   constexpr int NCn = NC<MHD>::ncons;
   const Lay L(cfg);
   int b, k, j, i;
@@ -391,6 +394,16 @@ __global__ void weighted_sum_kernel(const Real *x, const Real *y, Real w1, Real 
 }
 
 static unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// set while a stage is being captured into a CUDA graph (pb_stage_graph_create): the update kernels then read dt from
+// device memory instead of their by-value argument
+static const double *g_stage_dt_dev = nullptr;
+void set_stage_dt_pointer(const double *dt_dev) { g_stage_dt_dev = dt_dev; }
+
+__global__ void dt_control_kernel(const Real *est, Real cfl, Real *dt) {
+  const Real a = 2.0 * *dt, b = cfl * *est;
+  *dt = b < a ? b : a; // std::min(2 dt, cfl est), ref: parthenon driver.cpp:216-240
+}
 
 } // namespace pb
 
@@ -708,9 +721,9 @@ extern "C" int pb_update_from_sources(const pb_pack_t *pack, const pb_cfg_t *cfg
   const int T = 256;
   cudaStream_t s = (cudaStream_t)stream;
   if (cfg->mhd)
-    update_stream_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, gsrc, dudt_out);
+    update_stream_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, gsrc, dudt_out, g_stage_dt_dev);
   else
-    update_stream_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, gsrc, dudt_out);
+    update_stream_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, gsrc, dudt_out, g_stage_dt_dev);
   if (update_ghosts) {
     const Lay L(*cfg);
     const long long ntot = (long long)L.ncell * pack->nblocks;
@@ -728,13 +741,19 @@ extern "C" int pb_update_fused(const pb_pack_t *pack, const pb_cfg_t *cfg, const
   const int T = zone_threads();
   cudaStream_t s = (cudaStream_t)stream;
   if (cfg->mhd)
-    update_fused_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, dudt_out, gsrc_out);
+    update_fused_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, dudt_out, gsrc_out, g_stage_dt_dev);
   else
-    update_fused_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, dudt_out, gsrc_out);
+    update_fused_kernel<false><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, u0, ubase, beta, bdt, uout, dudt_out, gsrc_out, g_stage_dt_dev);
   if (update_ghosts) {
     const Lay L(*cfg);
     const long long ntot = (long long)L.ncell * pack->nblocks;
     update_ghost_kernel<<<grid_for(ntot, 256), 256, 0, s>>>(*cfg, pack->nblocks, 5 + 3 * cfg->mhd, u0, ubase, beta, uout);
   }
   return check_launch("update_fused_kernel");
+}
+
+extern "C" int pb_dt_control(const double *est_dev, double cfl, double *dt_dev, void *stream) {
+  if (!est_dev || !dt_dev) return set_error(PB_EINVAL, "pb_dt_control: NULL argument");
+  dt_control_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(est_dev, cfl, dt_dev);
+  return check_launch("dt_control_kernel");
 }

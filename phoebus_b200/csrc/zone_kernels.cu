@@ -434,6 +434,293 @@ __global__ void __launch_bounds__(128, 4) c2p_redo_kernel(const pb_pack_t pack, 
   }
 }
 
+// ------------------------------------------------------------------ ConToPrim::Solve as separate launches
+// The pack-level con2prim in three phases (option c2p_arith = 3, the default):
+//   c2p_solve_kernel    the root find only (setup + regula falsi): the long, divergent part. Small code, no primitive
+//                       state in registers. Writes the root into c2p_mu and one status byte per zone.
+//                       WARP-LEVEL HANDLING OF SLOWLY CONVERGING ZONES: after every iteration the warp votes; once at
+//                       most PB_C2P_DEFER lanes are still iterating, those lanes park their bracket state in a device
+//                       queue and the warp retires. c2p_slow_kernel resumes the parked zones, 32 slow zones per warp,
+//                       from exactly the saved state (RFState), so the bits do not depend on where a zone converged.
+//   c2p_unwrap_kernel   setup again + unwrap at the root + p2c (bounds used) or signal speeds, stores, fail flag, zone
+//                       flags: uniform work for every zone.
+//   c2p_redo_kernel     zones the fast arithmetic rejected: the whole solve (queued by the solve) or the unwrap only
+//                       (queued by the unwrap, bit 31 set) with the compiler's divide / sqrt.
+// Workspace (library-owned, grown on demand): status bytes, slow queue, iteration histogram.
+enum { C2S_OK = 0, C2S_NAN = 1, C2S_UNBRACKETED = 2, C2S_REDO = 3, C2S_SLOW = 4 };
+struct SlowEntry {
+  unsigned zone;
+  int it, b1, b2;
+  Real a, b, ya, yb, sign;
+};
+struct C2PWorkspace {
+  unsigned char *status;     // [nblocks * ncell]
+  SlowEntry *slow;           // parked root finds
+  unsigned *slow_count;      // entries appended by the current launch
+  unsigned slow_cap;
+  unsigned long long *stats; // optional (pb_c2p_stats): [0..31] iterations per solve, [32] solves that used a bound,
+                             // [33] failed solves, [34] zones parked, [35] zones solved
+};
+#ifndef PB_C2P_DEFER
+#define PB_C2P_DEFER 8
+#endif
+#ifndef PB_C2P_SOLVE_MINB
+#define PB_C2P_SOLVE_MINB 6
+#endif
+
+// geometry a root find needs: inverse 3-metric, spatial metric, sqrt(gamma) (no lapse / shift)
+struct SolveGeom {
+  Real detgam, gcov[10], gamcon[6];
+  PB_DEV Real g4(int m, int n) const { return gcov[flat4(m, n)]; }
+  PB_DEV Real gc3(int m, int n) const { return gamcon[flat4(m, n)]; }
+  PB_DEV void load(const GeomTab &g, int cell) {
+    detgam = g.at(0, G_DETGAM, cell);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int n = m; n < 3; ++n) gcov[flat4(m + 1, n + 1)] = g.at(0, G_GCOV + flat4(m + 1, n + 1), cell);
+#pragma unroll
+    for (int m = 0; m < 6; ++m) gamcon[m] = g.at(0, G_GAMCON + m, cell);
+  }
+};
+
+PB_DEV bool c2p_zone_of_index(const C2PWork &w, const Lay &L, long long t, int &b, int &k, int &j, int &i) {
+  if (w.shell) {
+    const Shell sh(L);
+    const int q = (int)(t / sh.n);
+    b = w.blocks ? w.blocks[q] : q;
+    sh.cell(L, (int)(t - (long long)q * sh.n), k, j, i);
+    return true;
+  }
+  const long long nreg = w.reg.n();
+  const int q = (int)(t / nreg);
+  b = w.blocks ? w.blocks[q] : q;
+  int rem = (int)(t - (long long)q * nreg);
+  i = w.reg.i0 + rem % w.reg.ni();
+  rem /= w.reg.ni();
+  j = w.reg.j0 + rem % w.reg.nj();
+  k = w.reg.k0 + rem / w.reg.nj();
+  return true;
+}
+
+template <bool MHD>
+__global__ void __launch_bounds__(128, PB_C2P_SOLVE_MINB) c2p_solve_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *__restrict__ cons,
+                                                                            const C2PWork work, const long long ntot, const C2PWorkspace ws,
+                                                                            const RedoQueue rq) {
+  constexpr int NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < ntot;
+  if (!valid) t = ntot - 1; // lanes past the end shadow the last zone (they take part in the warp votes, never store)
+  int b, k, j, i;
+  c2p_zone_of_index(work, L, t, b, k, j, i);
+  const int o = L.idx(k, j, i);
+  const unsigned zone = (unsigned)((long long)b * L.ncell + o);
+  const pb_block_t &blk = pack.blocks[b];
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  SolveGeom g;
+  g.load(gt, gt.cell(k, j, i));
+  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+  Real U[NCn];
+  load_comps<NCn>(cons + (size_t)b * NCn * L.ncell + o, L.ncell, U);
+  const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
+  ArithFast af;
+  C2PVars<MHD> s;
+  c2p_setup<MHD>(af, cfg, fc, g, U, s);
+  Residual<ArithFast> res = c2p_residual<MHD>(af, cfg, fc, s);
+  RFState st;
+  const Real guess = pack.c2p_mu[zone];
+  const bool bracketed = rf_begin(af, res, 0.0, 1.0, guess, st);
+  bool active = valid && !nan_in && bracketed && rf_running(st, cfg.c2p_tol, cfg.c2p_max_iter);
+  bool parked = false;
+  while (__any_sync(0xffffffffu, active)) {
+    if (active) {
+      rf_iterate(af, res, st);
+      active = rf_running(st, cfg.c2p_tol, cfg.c2p_max_iter);
+    }
+    const int nact = __popc(__ballot_sync(0xffffffffu, active));
+    if (nact > 0 && nact <= PB_C2P_DEFER) {
+      // a few stragglers hold the warp: park them (unless the fast arithmetic already rejected the zone, or the queue
+      // is full: then they simply finish here)
+      if (active && !af.failed()) {
+        const unsigned e = atomicAdd(ws.slow_count, 1u);
+        if (e < ws.slow_cap) {
+          SlowEntry &q = ws.slow[e];
+          q.zone = zone;
+          q.it = st.it, q.b1 = st.b1, q.b2 = st.b2;
+          q.a = st.a, q.b = st.b, q.ya = st.ya, q.yb = st.yb, q.sign = st.sign;
+          parked = true;
+          active = false;
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  unsigned char status;
+  if (nan_in) status = C2S_NAN;
+  else if (parked) status = C2S_SLOW;
+  else if (af.failed()) {
+    status = C2S_REDO;
+    rq.list[atomicAdd(rq.count, 1u)] = zone;
+  } else if (!bracketed) status = C2S_UNBRACKETED;
+  else {
+    status = C2S_OK;
+    pack.c2p_mu[zone] = 0.5 * (st.a + st.b);
+    if (ws.stats) atomicAdd(&ws.stats[st.it < 31 ? st.it : 31], 1ULL);
+  }
+  ws.status[zone] = status;
+  if (ws.stats && parked) atomicAdd(&ws.stats[34], 1ULL);
+}
+
+template <bool MHD>
+__global__ void __launch_bounds__(128, PB_C2P_SOLVE_MINB) c2p_slow_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *__restrict__ cons,
+                                                                           const C2PWorkspace ws, const RedoQueue rq) {
+  constexpr int NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  unsigned n = *ws.slow_count;
+  if (n > ws.slow_cap) n = ws.slow_cap;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const SlowEntry q = ws.slow[e];
+    const int b = (int)(q.zone / (unsigned)L.ncell), o = (int)(q.zone % (unsigned)L.ncell);
+    const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
+    const pb_block_t &blk = pack.blocks[b];
+    const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+    SolveGeom g;
+    g.load(gt, gt.cell(k, j, i));
+    const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+    Real U[NCn];
+    load_comps<NCn>(cons + (size_t)b * NCn * L.ncell + o, L.ncell, U);
+    ArithFast af;
+    C2PVars<MHD> s;
+    c2p_setup<MHD>(af, cfg, fc, g, U, s);
+    Residual<ArithFast> res = c2p_residual<MHD>(af, cfg, fc, s);
+    RFState st;
+    st.a = q.a, st.b = q.b, st.ya = q.ya, st.yb = q.yb, st.sign = q.sign;
+    st.it = q.it, st.b1 = q.b1, st.b2 = q.b2;
+    while (rf_running(st, cfg.c2p_tol, cfg.c2p_max_iter)) rf_iterate(af, res, st);
+    if (af.failed()) {
+      ws.status[q.zone] = C2S_REDO;
+      rq.list[atomicAdd(rq.count, 1u)] = q.zone;
+    } else {
+      ws.status[q.zone] = C2S_OK;
+      pack.c2p_mu[q.zone] = 0.5 * (st.a + st.b);
+      if (ws.stats) atomicAdd(&ws.stats[st.it < 31 ? st.it : 31], 1ULL);
+    }
+  }
+}
+
+// the unwrap of one solved zone with arithmetic policy AR; returns false if AR rejected an operand (nothing stored)
+template <bool MHD, class AR>
+PB_DEV bool c2p_unwrap_zone(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, const Lay &L, int b, int k, int j, int i,
+                            unsigned char *zflags, unsigned long long *stats) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  const int o = L.idx(k, j, i);
+  const pb_block_t &blk = pack.blocks[b];
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  Real U[NCn], P[NP], temp, sig[3];
+  load_comps<NCn>(z.cons, L.ncell, U);
+  const Real D0 = U[CRHO], S0 = U[CMOM], S1 = U[CMOM + 1], S2 = U[CMOM + 2], T0 = U[CENG];
+  AR ar;
+  C2PVars<MHD> s;
+  c2p_setup<MHD>(ar, cfg, fc, g, U, s);
+  Residual<AR> res = c2p_residual<MHD>(ar, cfg, fc, s);
+  const bool ok = c2p_unwrap<MHD>(ar, cfg, g, s, res, *z.mu, U, P, temp, sig);
+  if (ar.failed()) return false;
+  store_comps<NP>(z.prim, z.ncell, P);
+  *z.temp = temp;
+  for (int a = 0; a < L.ndim; ++a) z.csig[(size_t)a * z.ncell] = sig[a];
+  if (U[CRHO] != D0 || U[CMOM] != S0 || U[CMOM + 1] != S1 || U[CMOM + 2] != S2 || U[CENG] != T0 ||
+      isnan(U[CRHO]) || isnan(U[CMOM]) || isnan(U[CMOM + 1]) || isnan(U[CMOM + 2]) || isnan(U[CENG])) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * z.ncell] = U[n];
+  }
+  *z.fail = ok ? 1.0 : 0.0;
+  if (stats) {
+    if (res.used_bounds()) atomicAdd(&stats[32], 1ULL);
+    if (!ok) atomicAdd(&stats[33], 1ULL);
+    atomicAdd(&stats[35], 1ULL);
+  }
+  if (zflags) {
+    unsigned char f = ok ? 0 : ZF_FAIL;
+    if (cfg.enable_floors && floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_FLOOR;
+    zflags[(size_t)b * L.ncell + o] = f;
+  }
+  return true;
+}
+
+#ifndef PB_C2P_UNWRAP_MINB
+#define PB_C2P_UNWRAP_MINB 4
+#endif
+template <bool MHD>
+__global__ void __launch_bounds__(128, PB_C2P_UNWRAP_MINB) c2p_unwrap_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const C2PWork work,
+                                                                              const long long ntot, const C2PWorkspace ws, unsigned long long *err_count,
+                                                                              unsigned char *zflags, const RedoQueue rq) {
+  constexpr int NP = NC<MHD>::nprim;
+  const Lay L(cfg);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntot) return;
+  int b, k, j, i;
+  c2p_zone_of_index(work, L, t, b, k, j, i);
+  const int o = L.idx(k, j, i);
+  const unsigned zone = (unsigned)((long long)b * L.ncell + o);
+  const unsigned char status = ws.status[zone];
+  if (status == C2S_REDO) return;
+  if (status == C2S_OK) {
+    if (!c2p_unwrap_zone<MHD, ArithFast>(pack, cfg, cons, L, b, k, j, i, zflags, ws.stats))
+      rq.list[atomicAdd(rq.count, 1u)] = zone | 0x80000000u;
+    return;
+  }
+  // NaN guard: nothing written. Unbracketed root: p.bfield only (the reference aborts there; counted)
+  const ZonePtr<MHD> z(pack, cons, L, b, o);
+  const pb_block_t &blk = pack.blocks[b];
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  if (status == C2S_UNBRACKETED) {
+    if (MHD) {
+      const Real igdet = 1.0 / gt.at(0, G_DETGAM, gt.cell(k, j, i));
+#pragma unroll
+      for (int a = 0; a < 3; ++a) z.prim[(size_t)(PB_ + a) * z.ncell] = z.cons[(size_t)(CB + a) * z.ncell] * igdet;
+    }
+    if (err_count) atomicAdd(err_count, 1ULL);
+  }
+  *z.fail = 0.0;
+  if (ws.stats) atomicAdd(&ws.stats[33], 1ULL);
+  if (zflags) {
+    unsigned char f = ZF_FAIL;
+    if (cfg.enable_floors) {
+      PointGeom g;
+      g.load(gt, 0, gt.cell(k, j, i));
+      const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+      Real P[NP];
+      load_comps<NP>(z.prim, L.ncell, P);
+      if (floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_FLOOR;
+    }
+    zflags[(size_t)b * L.ncell + o] = f;
+  }
+}
+
+// rejected work of the split path: bit 31 clear = the whole zone (solve + unwrap) from the untouched guess, bit 31
+// set = the unwrap only (the root in c2p_mu is already exact), both with the compiler's divide / sqrt
+template <bool MHD>
+__global__ void __launch_bounds__(128, 4) c2p_split_redo_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons,
+                                                                unsigned long long *err_count, unsigned char *zflags, const RedoQueue rq,
+                                                                unsigned long long *stats) {
+  const Lay L(cfg);
+  const unsigned n = *rq.count;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(rq.total, (unsigned long long)n);
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const unsigned t = rq.list[e] & 0x7fffffffu;
+    const bool unwrap_only = (rq.list[e] & 0x80000000u) != 0;
+    const int b = (int)(t / (unsigned)L.ncell), o = (int)(t % (unsigned)L.ncell);
+    const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
+    if (unwrap_only) c2p_unwrap_zone<MHD, ArithExact>(pack, cfg, cons, L, b, k, j, i, zflags, stats);
+    else c2p_thread<MHD, 0>(pack, cfg, cons, L, b, k, j, i, err_count, zflags);
+  }
+}
+
 // ------------------------------------------------------------------ ConToPrim::Solve fixup
 // MODE 0: the task as the reference runs it (every interior zone reads its fail flag).
 // MODE 1 / 2: driven by the zone flags (post-c2p pass / stale-prim pass of region 7); the zone's
@@ -832,6 +1119,45 @@ unsigned long long *err_counter() {
 using namespace pb;
 
 namespace pb {
+// library-owned scratch of the split con2prim (grown on demand; stream-ordered use like the redo queue)
+static C2PWorkspace g_c2p_ws = {nullptr, nullptr, nullptr, 0, nullptr};
+static size_t g_c2p_ws_cells = 0;
+static unsigned long long *g_c2p_stats = nullptr; // allocated by pb_c2p_stats(enable)
+static bool g_c2p_stats_on = false;
+static int c2p_workspace(size_t cells, size_t nthr, C2PWorkspace &out) {
+  if (!g_c2p_ws.slow_count) {
+    if (cudaMalloc(&g_c2p_ws.slow_count, 16) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "c2p workspace");
+    cudaMemset(g_c2p_ws.slow_count, 0, 16);
+  }
+  const size_t cap = cells / 4 + 1024; // parked zones beyond the capacity simply finish in the solve kernel
+  if (cells > g_c2p_ws_cells) {
+    cudaDeviceSynchronize();
+    if (g_c2p_ws.status) cudaFree(g_c2p_ws.status);
+    if (g_c2p_ws.slow) cudaFree(g_c2p_ws.slow);
+    g_c2p_ws.status = nullptr;
+    g_c2p_ws.slow = nullptr;
+    if (cudaMalloc(&g_c2p_ws.status, cells) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "c2p status bytes");
+    if (cudaMalloc(&g_c2p_ws.slow, cap * sizeof(SlowEntry)) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "c2p slow queue");
+    g_c2p_ws.slow_cap = (unsigned)cap;
+    g_c2p_ws_cells = cells;
+  }
+  out = g_c2p_ws;
+  out.stats = g_c2p_stats_on ? g_c2p_stats : nullptr;
+  (void)nthr;
+  return PB_OK;
+}
+// everything the sequencer allocates lazily, sized for this pack up front (CUDA-graph capture may not allocate)
+int presize_workspaces(const pb_pack_t *pack, const pb_cfg_t *cfg) {
+  const Lay L(*cfg);
+  const size_t cells = (size_t)pack->nblocks * L.ncell;
+  RedoQueue rq;
+  int rc = redo_queue(cells, rq);
+  if (rc) return rc;
+  C2PWorkspace ws;
+  if ((rc = c2p_workspace(cells, cells, ws))) return rc;
+  if (!err_counter()) return set_cuda_error(cudaGetLastError(), "error counter");
+  return PB_OK;
+}
 // sequencer-internal launchers (abi_common.cu)
 static int launch_c2p_work(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const C2PWork &work, long long nthr,
                            unsigned char *zflags, cudaStream_t s) {
@@ -848,6 +1174,28 @@ static int launch_c2p_work(const pb_pack_t *pack, const pb_cfg_t *cfg, double *c
     if (rc) return rc;
     cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
   }
+  if (mode == 3) {
+    if ((long long)pack->nblocks * Lay(*cfg).ncell >= (1ll << 31)) return set_error(PB_EINVAL, "pack too large for the 31-bit redo queue");
+    int rc = redo_queue((size_t)nthr, rq);
+    if (rc) return rc;
+    C2PWorkspace ws;
+    if ((rc = c2p_workspace((size_t)pack->nblocks * Lay(*cfg).ncell, (size_t)nthr, ws))) return rc;
+    cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
+    cudaMemsetAsync(ws.slow_count, 0, sizeof(unsigned), s);
+    const int nsm = sm_count();
+    if (cfg->mhd) {
+      c2p_solve_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, nthr, ws, rq);
+      c2p_slow_kernel<true><<<nsm * PB_C2P_SOLVE_MINB, T, 0, s>>>(*pack, *cfg, cons, ws, rq);
+      c2p_unwrap_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, nthr, ws, err_counter(), zflags, rq);
+      c2p_split_redo_kernel<true><<<nsm * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq, ws.stats);
+    } else {
+      c2p_solve_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, nthr, ws, rq);
+      c2p_slow_kernel<false><<<nsm * PB_C2P_SOLVE_MINB, T, 0, s>>>(*pack, *cfg, cons, ws, rq);
+      c2p_unwrap_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, nthr, ws, err_counter(), zflags, rq);
+      c2p_split_redo_kernel<false><<<nsm * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq, ws.stats);
+    }
+    return check_launch("c2p_solve_kernel");
+  }
 #define PB_C2P(M, A) c2p_kernel<M, A><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, err_counter(), zflags, rq)
   if (cfg->mhd) {
     if (mode == 0) PB_C2P(true, 0); else if (mode == 1) PB_C2P(true, 1); else PB_C2P(true, 2);
@@ -856,8 +1204,8 @@ static int launch_c2p_work(const pb_pack_t *pack, const pb_cfg_t *cfg, double *c
   }
 #undef PB_C2P
   if (mode == 2) {
-    if (cfg->mhd) c2p_redo_kernel<true><<<148 * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq);
-    else c2p_redo_kernel<false><<<148 * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq);
+    if (cfg->mhd) c2p_redo_kernel<true><<<sm_count() * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq);
+    else c2p_redo_kernel<false><<<sm_count() * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq);
   }
   return check_launch("c2p_kernel");
 }
@@ -1014,4 +1362,21 @@ extern "C" int pb_estimate_dt(const pb_pack_t *pack, const pb_cfg_t *cfg, int ha
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
   dt_kernel<<<grid, T, 0, (cudaStream_t)stream>>>(*pack, *cfg, reg, has_face_speeds, dt_out);
   return check_launch("dt_kernel");
+}
+
+// Con2prim statistics of the split path (the reference's CON2PRIM_STATISTICS histogram, ref: src/fluid/con2prim_statistics.hpp:22-41,
+// con2prim_robust.hpp:377-379): enable != 0 starts counting (and zeroes the counters), enable == 0 stops. out_host (may be NULL):
+// 36 counters accumulated since they were last zeroed: [0..31] regula-falsi iterations per solve (31 = 31 or more), [32] solves
+// that used a floor / ceiling (conserved variables overwritten), [33] failed zones, [34] zones parked by the warp vote,
+// [35] zones unwrapped. Synchronises the device.
+extern "C" int pb_c2p_stats(int enable, unsigned long long out_host[36]) {
+  if (!g_c2p_stats) {
+    if (cudaMalloc(&g_c2p_stats, 36 * sizeof(unsigned long long)) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "pb_c2p_stats");
+    cudaMemset(g_c2p_stats, 0, 36 * sizeof(unsigned long long));
+  }
+  if (out_host && cudaMemcpy(out_host, g_c2p_stats, 36 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return set_cuda_error(cudaGetLastError(), "pb_c2p_stats");
+  if (enable && !g_c2p_stats_on) cudaMemset(g_c2p_stats, 0, 36 * sizeof(unsigned long long));
+  g_c2p_stats_on = enable != 0;
+  return PB_OK;
 }

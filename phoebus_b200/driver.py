@@ -3,8 +3,11 @@
 time-step control of Parthenon's EvolutionDriver (ref: external/parthenon/src/driver/driver.cpp:210-240,
 src/phoebus_driver.cpp:121-132).
 
-One process per GPU. With world > 1 the ghost exchange of region 8 is: local ghost copy + pack of
-the per-peer send buffers -> NCCL send/recv (torch.distributed batch_isend_irecv) -> unpack.
+One process per GPU. With world > 1 the ghost exchange of region 8 goes through the C ABI's NCCL path
+(pb_halo_exchange_begin / _end: pack -> grouped ncclSend / ncclRecv per peer on the communicator's stream -> unpack, with
+the same-GPU ghost copy and the interior con2prim issued in between); torch.distributed only carries the NCCL unique id
+to the ranks (and remains available as the transport with halo="torch"). use_graphs=True replays each RK stage as one
+CUDA graph (pb_stage_graph_*).
 """
 import ctypes as C
 
@@ -12,8 +15,12 @@ from . import _lib
 
 
 class FluidDriver:
-    def __init__(self, mesh, dist=None):
+    def __init__(self, mesh, dist=None, halo="nccl", use_graphs=False):
         self.m = mesh
+        self.halo_mode = halo
+        self.use_graphs = use_graphs
+        self.comm = None
+        self._graphs = {}
         self.L = _lib.lib()
         self.torch = mesh.torch
         self.dist = dist if mesh.world > 1 else None
@@ -29,6 +36,8 @@ class FluidDriver:
         self.force_split = False  # single GPU: sequence the stage as the multi-GPU path does (pre / halo + early c2p / post2)
         if self.dist is not None:
             self._setup_halo_buffers()
+            if self.halo_mode == "nccl":
+                self._setup_comm()
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -45,10 +54,41 @@ class FluidDriver:
         sp, stot, rp, rtot, peers = m.merged_halo_plans()
         self.sbuf = t.empty(max(stot, 1), dtype=t.float64, device=m.device)
         self.rbuf = t.empty(max(rtot, 1), dtype=t.float64, device=m.device)
-        self.halo = [dict(peer=peer, sbuf=self.sbuf[ss], rbuf=self.rbuf[rs]) for peer, ss, rs in peers]
+        self.halo = [dict(peer=peer, sbuf=self.sbuf[ss], rbuf=self.rbuf[rs], soff=ss.start, scnt=ss.stop - ss.start,
+                          roff=rs.start, rcnt=rs.stop - rs.start) for peer, ss, rs in peers]
         self.nsend, self.nrecv = len(sp), len(rp)
         self.splan = t.from_numpy(sp if len(sp) else np.zeros((1, 10), dtype=np.int32)).to(m.device)
         self.rplan = t.from_numpy(rp if len(rp) else np.zeros((1, 10), dtype=np.int32)).to(m.device)
+
+    def _setup_comm(self):
+        """NCCL communicator owned by the C library: rank 0 draws the unique id, torch.distributed broadcasts it"""
+        t, m, L = self.torch, self.m, self.L
+        buf = C.create_string_buffer(128)
+        if m.rank == 0:
+            _lib.check(L.pb_comm_unique_id(buf), "pb_comm_unique_id")
+        idt = t.tensor(list(buf.raw), dtype=t.uint8, device=m.device)
+        self.dist.broadcast(idt, 0)
+        raw = bytes(idt.cpu().tolist())
+        comm = C.c_void_p()
+        _lib.check(L.pb_comm_init(C.byref(comm), m.rank, m.world, raw), "pb_comm_init")
+        self.comm = comm
+        n = len(self.halo)
+        self._plan_arrays = ((C.c_int * n)(*[h["peer"] for h in self.halo]),
+                             (C.c_longlong * n)(*[h["soff"] for h in self.halo]), (C.c_longlong * n)(*[h["scnt"] for h in self.halo]),
+                             (C.c_longlong * n)(*[h["roff"] for h in self.halo]), (C.c_longlong * n)(*[h["rcnt"] for h in self.halo]))
+        pl = _lib.PbHaloPlan()
+        pl.send_plan, pl.nsend, pl.recv_plan, pl.nrecv = self.splan.data_ptr(), self.nsend, self.rplan.data_ptr(), self.nrecv
+        pl.send_buf, pl.recv_buf, pl.npeers = self.sbuf.data_ptr(), self.rbuf.data_ptr(), n
+        pl.peer, pl.send_off, pl.send_cnt, pl.recv_off, pl.recv_cnt = self._plan_arrays
+        self.plan = pl
+
+    def close(self):
+        for g in self._graphs.values():
+            self.L.pb_stage_graph_destroy(g)
+        self._graphs = {}
+        if self.comm is not None:
+            self.L.pb_comm_destroy(self.comm)
+            self.comm = None
 
     # ------------------------------------------------------------------ tasks
     def exchange(self, cons, under_transfer=None):
@@ -62,6 +102,13 @@ class FluidDriver:
             _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
             if under_transfer is not None:
                 under_transfer()
+            return
+        if self.comm is not None:
+            _lib.check(L.pb_halo_exchange_begin(pk, cfg, cons.data_ptr(), C.byref(self.plan), self.comm, s), "pb_halo_exchange_begin")
+            _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
+            if under_transfer is not None:
+                under_transfer()
+            _lib.check(L.pb_halo_exchange_end(pk, cfg, cons.data_ptr(), C.byref(self.plan), self.comm, s), "pb_halo_exchange_end")
             return
         dist = self.dist
         _lib.check(L.pb_halo_pack(pk, cfg, cons.data_ptr(), self.splan.data_ptr(), self.nsend, self.sbuf.data_ptr(), s), "pb_halo_pack")
@@ -98,6 +145,22 @@ class FluidDriver:
         base = m.cons["base"]
         cnt = C.c_void_p(m.counters.data_ptr())
         self.ensure_flags()
+        if self.use_graphs and self.timers is None and (self.dist is None or self.comm is not None) and not self.force_split:
+            # one CUDA graph per stage (container pair, beta); dt travels through device memory
+            if not hasattr(self, "dt_stage_dev"):
+                self.dt_stage_dev = self.torch.zeros(1, dtype=self.torch.float64, device=m.device)
+            self.dt_stage_dev.fill_(dt)
+            g = self._graphs.get(stage)
+            if g is None:
+                g = C.c_void_p()
+                _lib.check(L.pb_stage_graph_create(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta,
+                                                   self.dt_stage_dev.data_ptr(), cnt,
+                                                   C.byref(self.plan) if self.comm is not None else None, self.comm, s, C.byref(g)),
+                           "pb_stage_graph_create")
+                self._graphs[stage] = g
+            _lib.check(L.pb_stage_graph_launch(g, s), "pb_stage_graph_launch")
+            self.launches += self.LAUNCHES_PER_STAGE
+            return
         if self.dist is None and not self.force_split:
             _lib.check(L.pb_rk_stage(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s), "pb_rk_stage")
         else:
@@ -125,8 +188,8 @@ class FluidDriver:
         split = m.recon_lr is not None and self.L.pb_get_option(b"flux_split") == 1
         # flux: recon + riemann + riemann_redo per direction (split) or one fused launch; update; fixup; floors...
         n = m.ndim * (3 if split else 1) + 1 + 1 + 1 + 1
-        if self.L.pb_get_option(b"c2p_arith") == 2:
-            n += 1  # c2p_redo_kernel
+        kc = {0: 1, 1: 1, 2: 2, 3: 4}[self.L.pb_get_option(b"c2p_arith")]  # kernels per con2prim task (solve, slow, unwrap, redo)
+        n += kc - 1
         if m.gsrc is not None:
             n += 1
         if m.zflags is None:
@@ -141,7 +204,7 @@ class FluidDriver:
             n += 2
         if self.dist is not None:
             n += 2  # one pack and one unpack launch for all peers
-            n += 2 * (2 if self.L.pb_get_option(b"c2p_arith") == 2 else 1)  # c2p in three launches instead of one
+            n += 2 * kc  # c2p as three tasks (inner interiors, inner shells, boundary blocks) instead of one
         return n
 
     def enable_profile(self, on=True):
@@ -170,7 +233,9 @@ class FluidDriver:
         _lib.check(L.pb_estimate_dt(pk, cfg, int(self.has_face_speeds), m.dt_dev.data_ptr(), self._stream()), "pb_estimate_dt")
         self.has_face_speeds = True
         self.launches += 1
-        if self.dist is not None:
+        if self.comm is not None:
+            _lib.check(L.pb_comm_allreduce_min(self.comm, m.dt_dev.data_ptr(), 1, self._stream()), "pb_comm_allreduce_min")
+        elif self.dist is not None:
             self.dist.all_reduce(m.dt_dev, op=self.dist.ReduceOp.MIN)
         return m.p.cfl * float(m.dt_dev.item())
 

@@ -11,7 +11,7 @@ import re
 import subprocess
 import sys
 
-OURS = re.compile(r"recon_kernel|riemann_kernel|riemann_redo_kernel|c2p_redo_kernel|divb_kernel|history_kernel|c2p_fixup_packed_kernel|floors_packed_kernel|arith_selftest_kernel|flux_kernel|c2p_kernel|c2p_fixup_kernel|floors_kernel|flags_scan_kernel|update_\w+_kernel|source_kernel|"
+OURS = re.compile(r"pb::|recon_kernel|riemann_kernel|riemann_redo_kernel|c2p_redo_kernel|divb_kernel|history_kernel|c2p_fixup_packed_kernel|floors_packed_kernel|arith_selftest_kernel|flux_kernel|c2p_kernel|c2p_fixup_kernel|floors_kernel|flags_scan_kernel|update_\w+_kernel|source_kernel|"
                   r"divergence_kernel|emf_kernel|ct_flux_kernel|fix_fluxes_kernel|halo_\w+_kernel|bc_kernel|p2c_kernel|dt_kernel|"
                   r"weighted_sum_kernel")
 
@@ -86,5 +86,45 @@ def full(src, dst):
     print(open(dst).read()[:3000])
 
 
+def _num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return None
+
+
+def tojson(src, dst):
+    """profiles/ncu_kernel_metrics.json: per kernel (template arguments stripped) the averages over the captured launches of
+    dram bytes per launch, FP64-pipe utilisation, duration, registers, threads per instruction — what bench.py quotes"""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    acc = collections.OrderedDict()
+    for r in data:
+        name = re.sub(r"[<(].*", "", r[ix["Kernel Name"]]).replace("void ", "").replace("pb::", "").strip()
+        d = acc.setdefault(name, collections.defaultdict(list))
+        rd = _num(r[ix["dram__bytes_read.sum"]]) * scale.get(units[ix["dram__bytes_read.sum"]], 1.0)
+        wr = _num(r[ix["dram__bytes_write.sum"]]) * scale.get(units[ix["dram__bytes_write.sum"]], 1.0)
+        d["dram_bytes_per_launch"].append(rd + wr)
+        t = _num(r[ix["gpu__time_duration.sum"]])
+        u = units[ix["gpu__time_duration.sum"]]
+        d["duration_ms_under_ncu"].append(t * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1e-6))
+        for m, key in (("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
+                       ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+                       ("launch__registers_per_thread", "registers"),
+                       ("smsp__thread_inst_executed_per_inst_executed.ratio", "threads_per_instruction"),
+                       ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct")):
+            if m in ix and _num(r[ix[m]]) is not None:
+                d[key].append(_num(r[ix[m]]))
+    res = {"source": "profiles/%s (ncu --set full --clock-control none of `python bench.py`)" % dst.split("/")[-1].replace(".json", ".md"),
+           "kernels": {k: dict({kk: sum(v) / len(v) for kk, v in d.items()}, launches=len(d["dram_bytes_per_launch"])) for k, d in acc.items()}}
+    with open(dst, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res, indent=1)[:2500])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "json": tojson}[sys.argv[1]](sys.argv[2], sys.argv[3])

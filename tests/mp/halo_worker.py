@@ -43,42 +43,50 @@ def gpu_mode(periodic):
     # 8x4x4 MeshBlocks of 16^3: every rank owns blocks away from the mesh boundary, so the con2prim that runs
     # under the NCCL transfer (pb_rk_stage_post_early) is exercised
     fp = make_params((128, 64, 64), 16, periodic)
-    part = MeshPack(fp, device=dev, rank=rank, world=world)
     whole = MeshPack(fp, device=dev, rank=0, world=1)
-    d_part, d_whole = FluidDriver(part, dist), FluidDriver(whole)
-    bench.init_state(part, d_part)
+    d_whole = FluidDriver(whole)
     bench.init_state(whole, d_whole)
-    dt = 0.05 * d_whole.estimate_dt()
-    dtp = 0.05 * d_part.estimate_dt()
-    assert dt == dtp, (dt, dtp)
+    dt0 = 0.05 * d_whole.estimate_dt()
+    dts = [dt0]
     for cyc in range(3):
-        d_part.step(dt)
-        d_whole.step(dt)
-        dt2 = d_part.propose_dt(dt)
-        assert dt2 == d_whole.propose_dt(dt)
-        dt = dt2
+        d_whole.step(dts[-1])
+        dts.append(d_whole.propose_dt(dts[-1]))
     torch.cuda.synchronize()
     bad = 0
-    for n, lx in enumerate(part.lx):
-        m = whole.local_index[lx]
-        for name in ("prim", "temp", "c2p_mu", "fail", "csig"):
-            if not torch.equal(getattr(part, name)[n], getattr(whole, name)[m]):
+    # the brick of this rank, three ways: NCCL through the C ABI (pb_halo_exchange_begin / _end), the same with every stage
+    # replayed as a CUDA graph, and torch.distributed as the transport
+    for halo, graphs in (("nccl", False), ("nccl", True), ("torch", False)):
+        part = MeshPack(fp, device=dev, rank=rank, world=world)
+        d_part = FluidDriver(part, dist, halo=halo, use_graphs=graphs)
+        bench.init_state(part, d_part)
+        dt = 0.05 * d_part.estimate_dt()
+        assert dt == dt0, (dt, dt0)
+        for cyc in range(3):
+            d_part.step(dt)
+            dt = d_part.propose_dt(dt)
+            assert dt == dts[cyc + 1], (halo, graphs, cyc, dt, dts[cyc + 1])
+        torch.cuda.synchronize()
+        for n, lx in enumerate(part.lx):
+            m = whole.local_index[lx]
+            for name in ("prim", "temp", "c2p_mu", "fail", "csig"):
+                if not torch.equal(getattr(part, name)[n], getattr(whole, name)[m]):
+                    bad += 1
+                    print("rank", rank, halo, graphs, "block", lx, name, "differs", flush=True)
+            if not torch.equal(part.cons["base"][n], whole.cons["base"][m]):
                 bad += 1
-                print("rank", rank, "block", lx, name, "differs", flush=True)
-        if not torch.equal(part.cons["base"][n], whole.cons["base"][m]):
+                print("rank", rank, halo, graphs, "block", lx, "cons differs", flush=True)
+        cnt = part.counters.clone()
+        dist.all_reduce(cnt)
+        if not torch.equal(cnt, whole.counters):
             bad += 1
-            print("rank", rank, "block", lx, "cons differs", flush=True)
-    if not torch.equal(part.counters, part.counters):
-        bad += 1
-    cnt = part.counters.clone()
-    dist.all_reduce(cnt)
-    if not torch.equal(cnt, whole.counters):
-        bad += 1
-        print("rank", rank, "floor counters differ", cnt.tolist(), whole.counters.tolist(), flush=True)
+            print("rank", rank, halo, graphs, "floor counters differ", cnt.tolist(), whole.counters.tolist(), flush=True)
+        d_part.close()
+        nblocks, rgrid = part.nblocks, part.rgrid
+        del part, d_part
     t = torch.tensor([bad], device=dev)
     dist.all_reduce(t)
     if rank == 0:
-        print("MP_RESULT bad=%d blocks_per_rank=%d grid=%s" % (int(t.item()), part.nblocks, part.rgrid), flush=True)
+        print("MP_RESULT bad=%d blocks_per_rank=%d grid=%s variants=nccl_c,nccl_c+graphs,torch" % (int(t.item()), nblocks, rgrid), flush=True)
     return int(t.item())
 
 

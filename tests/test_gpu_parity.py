@@ -313,7 +313,7 @@ def test_redo_queues_reproduce_exact_arithmetic(name):
     results = []
     redo0 = L.pb_arith_redo_count()
     try:
-        for flux_split, c2p_arith in ((1, 2), (0, 0)):
+        for flux_split, c2p_arith in ((1, 3), (0, 0), (1, 2)):
             L.pb_set_option(b"flux_split", flux_split)
             L.pb_set_option(b"c2p_arith", c2p_arith)
             mesh, fp = product_mesh(g, device=_dev())
@@ -329,10 +329,11 @@ def test_redo_queues_reproduce_exact_arithmetic(name):
             results.append({k: _np(getattr(mesh, k)).copy() for k in ("flux", "fsig", "prim", "c2p_mu", "fail", "csig", "temp")})
     finally:
         L.pb_set_option(b"flux_split", 1)
-        L.pb_set_option(b"c2p_arith", 2)
+        L.pb_set_option(b"c2p_arith", 3)
     assert L.pb_arith_redo_count() > redo0, "the test state did not exercise the redo kernels"
     for k in results[0]:
         assert np.array_equal(results[0][k], results[1][k], equal_nan=True), k
+        assert np.array_equal(results[0][k], results[2][k], equal_nan=True), k
 
 
 @pytest.mark.parametrize("name", ["linmodes2d_long", "linmodes3d_long"])
@@ -659,3 +660,64 @@ def test_hashed_fixture_with_32cube_meshblocks():
         m = h.manifest(tag)
         drv.stage(m["stage"], m["dt"])
         check(tag, m["sc1"])
+
+
+@pytest.mark.parametrize("name", ["torus2d_fail", "torus3d", "blast3d"])
+def test_con2prim_variants_bit_identical_and_statistics(name):
+    """the split con2prim (root find / parked slow zones / unwrap / redo as separate launches, the default) against the
+    single-kernel variants on two full cycles of state evolution, and the statistics it keeps (the reference's
+    CON2PRIM_STATISTICS histogram): every solved zone is counted exactly once"""
+    import torch
+    from phoebus_b200 import _lib
+    L = _lib.lib()
+    out = {}
+    stats = (C.c_ulonglong * 36)()
+    try:
+        for mode in (3, 2, 0):
+            L.pb_set_option(b"c2p_arith", mode)
+            g, p, mesh, drv, order = _setup(name)
+            if mode == 3:
+                _lib.check(L.pb_c2p_stats(1, None), "pb_c2p_stats")
+            for tag in stage_tags(g):
+                man = g.manifest(tag)
+                drv.stage(man["stage"], man["dt"])
+            torch.cuda.synchronize()
+            if mode == 3:
+                _lib.check(L.pb_c2p_stats(0, stats), "pb_c2p_stats")
+            out[mode] = {k: _np(getattr(mesh, k)).copy() for k in FIELDS}
+            out[mode]["cons"] = _np(mesh.cons["base"]).copy()
+            nstage, ncells = len(stage_tags(g)), mesh.nblocks * mesh.ncell
+    finally:
+        L.pb_set_option(b"c2p_arith", 3)
+    for mode in (2, 0):
+        for k in out[3]:
+            assert np.array_equal(out[3][k], out[mode][k], equal_nan=True), (name, mode, k)
+    st = list(stats)
+    assert st[35] + st[33] >= nstage * ncells > 0          # every zone of every entire-domain solve (+ floors' re-solves excluded)
+    assert sum(st[:32]) >= st[35] - (st[35] // 10) - 1     # iteration histogram covers the fast-path solves
+    if name == "torus2d_fail":
+        assert st[33] > 100 and st[32] > 100               # failures and bound hits are really there
+
+
+@pytest.mark.parametrize("name", ["torus3d", "blast3d", "shocktube"])
+def test_cuda_graph_replay_matches_reference_dumps(name):
+    """every RK stage replayed as one CUDA graph (pb_stage_graph_*, dt through device memory): the reference's dumps, bit for bit"""
+    from phoebus_b200.driver import FluidDriver
+    g, p = load_case(name)
+    mesh, fp = product_mesh(g, device=_dev())
+    order = load_product_state(mesh, g, "init")
+    drv = FluidDriver(mesh, use_graphs=True)
+    drv.has_face_speeds = True
+    for tag in stage_tags(g):
+        man = g.manifest(tag)
+        drv.stage(man["stage"], man["dt"])
+        mesh.torch.cuda.synchronize()
+        for mb in man["blocks"]:
+            n = order[mb["gid"]]
+            ref = fd.ref_state(getter(g, tag), mb["gid"], mesh.shape, man["sc1"])
+            for k in FIELDS:
+                mine = _np(getattr(mesh, k)[n]).reshape(ref[k].shape)
+                assert np.array_equal(mine, ref[k], equal_nan=True), (name, tag, mb["gid"], k, fd.relerr(mine, ref[k]))
+            assert np.array_equal(_np(mesh.cons[man["sc1"]][n]), ref["cons"], equal_nan=True), (name, tag, mb["gid"], "cons")
+    assert len(drv._graphs) == min(2, len(stage_tags(g)))
+    drv.close()
