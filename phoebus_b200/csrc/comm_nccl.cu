@@ -201,6 +201,7 @@ extern "C" int pb_stage_graph_create(const pb_pack_t *pack, const pb_cfg_t *cfg,
   if (rc) return rc;
   if (!graph_out || !dt_dev || !sc0 || !base || !sc1) return set_error(PB_EINVAL, "pb_stage_graph_create: NULL argument");
   if (comm && (rc = check_plan(plan, comm))) return rc;
+  if (!stream) return set_error(PB_EINVAL, "pb_stage_graph_create: stream capture needs a non-default stream");
   if ((rc = presize_workspaces(pack, cfg))) return rc; // no allocation may happen inside the capture
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);

@@ -462,8 +462,23 @@ struct C2PWorkspace {
                              // [33] failed solves, [34] zones parked, [35] zones solved
 };
 #ifndef PB_C2P_DEFER
-#define PB_C2P_DEFER 8
+#define PB_C2P_DEFER 4 // park when at most this many lanes of the warp are still iterating ...
 #endif
+#ifndef PB_C2P_DEFER_IT
+#define PB_C2P_DEFER_IT 3 // ... and they have done at least this many iterations (1 - 3 iterations are the norm, measured)
+#endif
+// statistics are summed per CTA in shared memory and flushed with one atomic per non-empty counter
+constexpr int C2P_NSTAT = 36;
+PB_DEV void stats_begin(unsigned *s_stat) {
+  for (int q = threadIdx.x; q < C2P_NSTAT; q += blockDim.x) s_stat[q] = 0;
+  __syncthreads();
+}
+PB_DEV void stats_end(const unsigned *s_stat, unsigned long long *stats) {
+  __syncthreads();
+  if (stats)
+    for (int q = threadIdx.x; q < C2P_NSTAT; q += blockDim.x)
+      if (s_stat[q]) atomicAdd(&stats[q], (unsigned long long)s_stat[q]);
+}
 #ifndef PB_C2P_SOLVE_MINB
 #define PB_C2P_SOLVE_MINB 6
 #endif
@@ -508,6 +523,8 @@ __global__ void __launch_bounds__(128, PB_C2P_SOLVE_MINB) c2p_solve_kernel(const
                                                                             const C2PWork work, const long long ntot, const C2PWorkspace ws,
                                                                             const RedoQueue rq) {
   constexpr int NCn = NC<MHD>::ncons;
+  __shared__ unsigned s_stat[C2P_NSTAT];
+  stats_begin(s_stat);
   const Lay L(cfg);
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = t < ntot;
@@ -539,7 +556,7 @@ __global__ void __launch_bounds__(128, PB_C2P_SOLVE_MINB) c2p_solve_kernel(const
       active = rf_running(st, cfg.c2p_tol, cfg.c2p_max_iter);
     }
     const int nact = __popc(__ballot_sync(0xffffffffu, active));
-    if (nact > 0 && nact <= PB_C2P_DEFER) {
+    if (nact > 0 && nact <= PB_C2P_DEFER && st.it >= PB_C2P_DEFER_IT) {
       // a few stragglers hold the warp: park them (unless the fast arithmetic already rejected the zone, or the queue
       // is full: then they simply finish here)
       if (active && !af.failed()) {
@@ -555,21 +572,23 @@ __global__ void __launch_bounds__(128, PB_C2P_SOLVE_MINB) c2p_solve_kernel(const
       }
     }
   }
-  if (!valid) return;
-  unsigned char status;
-  if (nan_in) status = C2S_NAN;
-  else if (parked) status = C2S_SLOW;
-  else if (af.failed()) {
-    status = C2S_REDO;
-    rq.list[atomicAdd(rq.count, 1u)] = zone;
-  } else if (!bracketed) status = C2S_UNBRACKETED;
-  else {
-    status = C2S_OK;
-    pack.c2p_mu[zone] = 0.5 * (st.a + st.b);
-    if (ws.stats) atomicAdd(&ws.stats[st.it < 31 ? st.it : 31], 1ULL);
+  if (valid) {
+    unsigned char status;
+    if (nan_in) status = C2S_NAN;
+    else if (parked) status = C2S_SLOW;
+    else if (af.failed()) {
+      status = C2S_REDO;
+      rq.list[atomicAdd(rq.count, 1u)] = zone;
+    } else if (!bracketed) status = C2S_UNBRACKETED;
+    else {
+      status = C2S_OK;
+      pack.c2p_mu[zone] = 0.5 * (st.a + st.b);
+      if (ws.stats) atomicAdd(&s_stat[st.it < 31 ? st.it : 31], 1u);
+    }
+    ws.status[zone] = status;
+    if (ws.stats && parked) atomicAdd(&s_stat[34], 1u);
   }
-  ws.status[zone] = status;
-  if (ws.stats && parked) atomicAdd(&ws.stats[34], 1ULL);
+  stats_end(s_stat, ws.stats);
 }
 
 template <bool MHD>
@@ -612,7 +631,7 @@ __global__ void __launch_bounds__(128, PB_C2P_SOLVE_MINB) c2p_slow_kernel(const 
 // the unwrap of one solved zone with arithmetic policy AR; returns false if AR rejected an operand (nothing stored)
 template <bool MHD, class AR>
 PB_DEV bool c2p_unwrap_zone(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, const Lay &L, int b, int k, int j, int i,
-                            unsigned char *zflags, unsigned long long *stats) {
+                            unsigned char *zflags, unsigned *stats) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
   const int o = L.idx(k, j, i);
   const pb_block_t &blk = pack.blocks[b];
@@ -639,10 +658,10 @@ PB_DEV bool c2p_unwrap_zone(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *co
     for (int n = 0; n < 5; ++n) z.cons[(size_t)n * z.ncell] = U[n];
   }
   *z.fail = ok ? 1.0 : 0.0;
-  if (stats) {
-    if (res.used_bounds()) atomicAdd(&stats[32], 1ULL);
-    if (!ok) atomicAdd(&stats[33], 1ULL);
-    atomicAdd(&stats[35], 1ULL);
+  if (stats) { // shared-memory counters of the CTA
+    if (res.used_bounds()) atomicAdd(&stats[32], 1u);
+    if (!ok) atomicAdd(&stats[33], 1u);
+    atomicAdd(&stats[35], 1u);
   }
   if (zflags) {
     unsigned char f = ok ? 0 : ZF_FAIL;
@@ -652,17 +671,12 @@ PB_DEV bool c2p_unwrap_zone(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *co
   return true;
 }
 
-#ifndef PB_C2P_UNWRAP_MINB
-#define PB_C2P_UNWRAP_MINB 4
-#endif
+// one thread of the unwrap launch: dispatch on the status byte the solve left
 template <bool MHD>
-__global__ void __launch_bounds__(128, PB_C2P_UNWRAP_MINB) c2p_unwrap_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const C2PWork work,
-                                                                              const long long ntot, const C2PWorkspace ws, unsigned long long *err_count,
-                                                                              unsigned char *zflags, const RedoQueue rq) {
+PB_DEV void c2p_unwrap_thread(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *cons, const C2PWork &work, const Lay &L, long long t,
+                              const C2PWorkspace &ws, unsigned long long *err_count, unsigned char *zflags, const RedoQueue &rq,
+                              unsigned *s_stat) {
   constexpr int NP = NC<MHD>::nprim;
-  const Lay L(cfg);
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntot) return;
   int b, k, j, i;
   c2p_zone_of_index(work, L, t, b, k, j, i);
   const int o = L.idx(k, j, i);
@@ -670,7 +684,7 @@ __global__ void __launch_bounds__(128, PB_C2P_UNWRAP_MINB) c2p_unwrap_kernel(con
   const unsigned char status = ws.status[zone];
   if (status == C2S_REDO) return;
   if (status == C2S_OK) {
-    if (!c2p_unwrap_zone<MHD, ArithFast>(pack, cfg, cons, L, b, k, j, i, zflags, ws.stats))
+    if (!c2p_unwrap_zone<MHD, ArithFast>(pack, cfg, cons, L, b, k, j, i, zflags, s_stat))
       rq.list[atomicAdd(rq.count, 1u)] = zone | 0x80000000u;
     return;
   }
@@ -687,7 +701,7 @@ __global__ void __launch_bounds__(128, PB_C2P_UNWRAP_MINB) c2p_unwrap_kernel(con
     if (err_count) atomicAdd(err_count, 1ULL);
   }
   *z.fail = 0.0;
-  if (ws.stats) atomicAdd(&ws.stats[33], 1ULL);
+  if (s_stat) atomicAdd(&s_stat[33], 1u);
   if (zflags) {
     unsigned char f = ZF_FAIL;
     if (cfg.enable_floors) {
@@ -700,6 +714,21 @@ __global__ void __launch_bounds__(128, PB_C2P_UNWRAP_MINB) c2p_unwrap_kernel(con
     }
     zflags[(size_t)b * L.ncell + o] = f;
   }
+}
+
+#ifndef PB_C2P_UNWRAP_MINB
+#define PB_C2P_UNWRAP_MINB 4
+#endif
+template <bool MHD>
+__global__ void __launch_bounds__(128, PB_C2P_UNWRAP_MINB) c2p_unwrap_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const C2PWork work,
+                                                                              const long long ntot, const C2PWorkspace ws, unsigned long long *err_count,
+                                                                              unsigned char *zflags, const RedoQueue rq) {
+  __shared__ unsigned s_stat[C2P_NSTAT];
+  stats_begin(s_stat);
+  const Lay L(cfg);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ntot) c2p_unwrap_thread<MHD>(pack, cfg, cons, work, L, t, ws, err_count, zflags, rq, ws.stats ? s_stat : nullptr);
+  stats_end(s_stat, ws.stats);
 }
 
 // rejected work of the split path: bit 31 clear = the whole zone (solve + unwrap) from the untouched guess, bit 31
@@ -716,8 +745,9 @@ __global__ void __launch_bounds__(128, 4) c2p_split_redo_kernel(const pb_pack_t 
     const bool unwrap_only = (rq.list[e] & 0x80000000u) != 0;
     const int b = (int)(t / (unsigned)L.ncell), o = (int)(t % (unsigned)L.ncell);
     const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
-    if (unwrap_only) c2p_unwrap_zone<MHD, ArithExact>(pack, cfg, cons, L, b, k, j, i, zflags, stats);
+    if (unwrap_only) c2p_unwrap_zone<MHD, ArithExact>(pack, cfg, cons, L, b, k, j, i, zflags, nullptr);
     else c2p_thread<MHD, 0>(pack, cfg, cons, L, b, k, j, i, err_count, zflags);
+    if (stats) atomicAdd(&stats[35], 1ULL); // redone zones: counted as solved, not in the histogram
   }
 }
 

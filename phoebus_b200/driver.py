@@ -146,19 +146,27 @@ class FluidDriver:
         cnt = C.c_void_p(m.counters.data_ptr())
         self.ensure_flags()
         if self.use_graphs and self.timers is None and (self.dist is None or self.comm is not None) and not self.force_split:
-            # one CUDA graph per stage (container pair, beta); dt travels through device memory
+            # one CUDA graph per stage (container pair, beta); dt travels through device memory. Capture needs a real
+            # stream (not the legacy default one), so graph mode runs on its own stream, ordered after / before the caller's.
+            t = self.torch
             if not hasattr(self, "dt_stage_dev"):
-                self.dt_stage_dev = self.torch.zeros(1, dtype=self.torch.float64, device=m.device)
-            self.dt_stage_dev.fill_(dt)
-            g = self._graphs.get(stage)
-            if g is None:
-                g = C.c_void_p()
-                _lib.check(L.pb_stage_graph_create(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta,
-                                                   self.dt_stage_dev.data_ptr(), cnt,
-                                                   C.byref(self.plan) if self.comm is not None else None, self.comm, s, C.byref(g)),
-                           "pb_stage_graph_create")
-                self._graphs[stage] = g
-            _lib.check(L.pb_stage_graph_launch(g, s), "pb_stage_graph_launch")
+                self.dt_stage_dev = t.zeros(1, dtype=t.float64, device=m.device)
+                self._gstream = t.cuda.Stream(device=m.device)
+            cur = t.cuda.current_stream()
+            self._gstream.wait_stream(cur)
+            with t.cuda.stream(self._gstream):
+                gs = C.c_void_p(self._gstream.cuda_stream)
+                self.dt_stage_dev.fill_(dt)
+                g = self._graphs.get(stage)
+                if g is None:
+                    g = C.c_void_p()
+                    _lib.check(L.pb_stage_graph_create(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta,
+                                                       self.dt_stage_dev.data_ptr(), cnt,
+                                                       C.byref(self.plan) if self.comm is not None else None, self.comm, gs, C.byref(g)),
+                               "pb_stage_graph_create")
+                    self._graphs[stage] = g
+                _lib.check(L.pb_stage_graph_launch(g, gs), "pb_stage_graph_launch")
+            cur.wait_stream(self._gstream)
             self.launches += self.LAUNCHES_PER_STAGE
             return
         if self.dist is None and not self.force_split:
