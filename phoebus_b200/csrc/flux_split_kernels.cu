@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
 
 // One face: load both states and the face geometry, prim_to_flux on each, LLF / HLL, store.
 // Returns the arithmetic policy's failure flag (always false for ArithExact).
-template <int DIR, bool MHD, class AR>
+#ifndef PB_RIEMANN_BZ
+#define PB_RIEMANN_BZ 1
+#endif
+template <int DIR, bool MHD, class AR, bool BZFAST = (PB_RIEMANN_BZ != 0)>
 PB_DEV bool riemann_face(const pb_pack_t &pack, const pb_cfg_t &cfg, const Lay &L, const Real *__restrict__ ql,
                          const Real *__restrict__ qr, int b, int k, int j, int i) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
@@ -137,8 +140,22 @@ PB_DEV bool riemann_face(const pb_pack_t &pack, const pb_cfg_t &cfg, const Lay &
 
   Real Ul[NCn], Fl[NCn], Ur[NCn], Fr[NCn], vml, vpl, vmr, vpr;
   AR ar;
-  prim_to_flux<DIR, MHD>(ar, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
-  prim_to_flux<DIR, MHD>(ar, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+  // unmagnetised faces (both states have B == +-0 in all components) take the exact hydrodynamic variant of
+  // prim_to_flux; the decision is made per warp so that the two code paths never run side by side
+  bool bzero = false;
+  if (MHD && BZFAST) {
+    long long any = 0;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) any |= __double_as_longlong(qL[PB_ + m]) | __double_as_longlong(qR[PB_ + m]);
+    bzero = __all_sync(__activemask(), (any << 1) == 0);
+  }
+  if (bzero) {
+    prim_to_flux<DIR, MHD, true>(ar, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
+    prim_to_flux<DIR, MHD, true>(ar, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+  } else {
+    prim_to_flux<DIR, MHD, false>(ar, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
+    prim_to_flux<DIR, MHD, false>(ar, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
+  }
   Real *fl = pack.flux + ((size_t)b * L.ndim + (DIR - 1)) * NCn * L.ncell + o;
   Real speed;
   if (cfg.riemann == 0) { // llf, ref: riemann.hpp:256-276
@@ -198,7 +215,7 @@ __global__ void __launch_bounds__(128) riemann_redo_kernel(const pb_pack_t pack,
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     int b, k, j, i;
     face_of_index(reg, (long long)rq.list[e], b, k, j, i);
-    riemann_face<DIR, MHD, ArithExact>(pack, cfg, L, ql, qr, b, k, j, i);
+    riemann_face<DIR, MHD, ArithExact, false>(pack, cfg, L, ql, qr, b, k, j, i);
   }
 }
 
