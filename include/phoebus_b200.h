@@ -19,6 +19,9 @@
  *    ref: src/fluid/fluid.cpp:506-514), never an error code.
  *  - Entry points never allocate field memory and never synchronise the stream, except the
  *    *_host convenience calls, which say so.
+ *  - The library keeps small device work spaces of its own (redo queues, con2prim scratch, counters): they belong to
+ *    ONE device per process and are used in stream order, i.e. one stage in flight at a time. A call from another
+ *    device, or on another stream while the previous one still has work queued, returns PB_EINVAL.
  */
 #ifndef PHOEBUS_B200_H_
 #define PHOEBUS_B200_H_
@@ -334,18 +337,25 @@ int pb_profile_read(double ms[PB_NTASK], int calls[PB_NTASK]);
 
 /* Run-time options of the library (initial values from the environment variables in parentheses):
  *   "flux_split" 1|0  (PB_FLUX_MODE=split|fused)  two-launch flux path when the pack has recon_lr, else the fused kernel
- *   "c2p_arith"  3|2|0|1 (PB_C2P_ARITH=split|queue|exact|inline) con2prim: root find and unwrap as separate launches with
- *                warp-level parking of slowly converging zones (default); one kernel with ArithFast + redo queue; the
- *                compiler's divide / sqrt; ArithFast with an inline exact re-solve. All settings produce identical bits. */
+ *   "flux_tma"   1|0  (PB_FLUX_STAGE=tma|cpasync) the fused flux kernel stages its stencil tile with one TMA tensor load
+ *                (cp.async.bulk.tensor, 5-D box of the primitive slab) per CTA, or with per-thread cp.async copies
+ *   "c2p_arith"  2|3|0|1 (PB_C2P_ARITH=queue|split|exact|inline) con2prim: one launch with warp-level parking of slowly
+ *                converging zones + redo queue for the zones ArithFast rejects (default); root find and unwrap as separate
+ *                launches (same parking); the compiler's divide / sqrt; ArithFast with an inline exact re-solve.
+ *                All settings produce identical bits. */
 int pb_set_option(const char *key, int value);
 int pb_get_option(const char *key);
 /* Faces / zones that the fast arithmetic rejected and riemann_redo_kernel / c2p_redo_kernel recomputed with the compiler's divide / sqrt,
  * accumulated since the library was loaded (synchronises the device). */
 unsigned long long pb_arith_redo_count(void);
+/* Unbracketed con2prim roots counted since the library was loaded or last reset. The reference aborts the run on the first
+ * one (PARTHENON_FAIL, ref: src/phoebus_utils/root_find.hpp:115-118); here the zone is marked failed and the caller decides.
+ * Negative on error. Synchronises the device. */
+long long pb_c2p_unbracketed_count(int reset);
 /* Con2prim statistics (the reference's CON2PRIM_STATISTICS histogram, ref: src/fluid/con2prim_statistics.hpp:22-41): enable != 0
  * starts counting (zeroing the counters), 0 stops; out_host (may be NULL) receives the 36 counters accumulated so far:
  * [0..31] regula-falsi iterations per solve (31 = 31 or more), [32] solves that used a floor / ceiling, [33] failed zones,
- * [34] zones parked by the warp vote, [35] zones unwrapped. Counted by the split con2prim path only. Synchronises the device. */
+ * [34] zones parked by the warp vote, [35] zones unwrapped. Counted by the default (2) and the split (3) con2prim paths. Synchronises the device. */
 int pb_c2p_stats(int enable, unsigned long long out_host[36]);
 /* Same idea one level up: riemann.hpp's prim_to_flux (face state -> U, F, v+-) evaluated with the
  * deferred-branch arithmetic and with the compiler's, on n synthetic MHD face states (flat != 0:

@@ -111,6 +111,7 @@ SYMBOLS = {
     "pb_selftest_arith": (C.c_int, [C.c_longlong, C.c_ulonglong, C.c_int, _P, _P]),
     "pb_arith_redo_count": (C.c_ulonglong, []),
     "pb_c2p_stats": (C.c_int, [C.c_int, _P]),
+    "pb_c2p_unbracketed_count": (C.c_longlong, [C.c_int]),
     "pb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "pb_get_option": (C.c_int, [C.c_char_p]),
     "pb_selftest_riemann": (C.c_int, [C.c_longlong, C.c_ulonglong, _CFG, C.c_int, _P, _P, _P]),

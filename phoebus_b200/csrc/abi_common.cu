@@ -2,6 +2,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
+#include <utility>
 #include <vector>
 
 #include "pb_device.cuh"
@@ -38,6 +40,17 @@ int check_args(const pb_pack_t *pack, const pb_cfg_t *cfg) {
   if (cfg->floor_type < 0 || cfg->floor_type > 4) return set_error(PB_EINVAL, "unknown floor type");
   return PB_OK;
 }
+// entry points validate the pack fields they dereference: a partly filled pb_pack_t is an argument error, not an
+// asynchronous illegal-address fault
+int need_fields(const char *entry, std::initializer_list<std::pair<const void *, const char *>> fields) {
+  for (const auto &f : fields)
+    if (!f.first) {
+      char msg[160];
+      snprintf(msg, sizeof msg, "%s: pack->%s is NULL", entry, f.second);
+      return set_error(PB_EINVAL, msg);
+    }
+  return PB_OK;
+}
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   if (!v || !*v) return dflt;
@@ -56,7 +69,7 @@ static int g_flux_split = [] {
 }();
 static int g_c2p_arith = [] {
   const char *e = getenv("PB_C2P_ARITH");
-  return (e && e[0] == 'e') ? 0 : ((e && e[0] == 'i') ? 1 : ((e && e[0] == 'q') ? 2 : 3));
+  return (e && e[0] == 'e') ? 0 : ((e && e[0] == 'i') ? 1 : ((e && e[0] == 's') ? 3 : 2));
 }();
 int sm_count() {
   static int n = [] {
@@ -66,7 +79,12 @@ int sm_count() {
   }();
   return n;
 }
+static int g_flux_tma = [] {
+  const char *e = getenv("PB_FLUX_STAGE");
+  return (e && e[0] == 'c') ? 0 : 1; // cpasync | tma (default)
+}();
 bool flux_split_enabled() { return g_flux_split != 0; }
+bool flux_tma_enabled() { return g_flux_tma != 0; }
 int c2p_arith_mode() { return g_c2p_arith; }
 int zone_threads() {
   static int v = env_int("PB_ZONE_THREADS", 128);
@@ -79,9 +97,9 @@ using namespace pb;
 
 extern "C" const char *pb_version(void) { return "phoebus_b200 0.1 (sm_100a, fp64, fmad=off)"; }
 extern "C" const char *pb_last_error(void) { return g_err; }
-extern "C" int pb_nprim(const pb_cfg_t *cfg) { return 7 + 3 * cfg->mhd; }
-extern "C" int pb_ncons(const pb_cfg_t *cfg) { return 5 + 3 * cfg->mhd; }
-extern "C" long long pb_cells_per_block(const pb_cfg_t *cfg) { return Lay(*cfg).ncell; }
+extern "C" int pb_nprim(const pb_cfg_t *cfg) { return cfg ? 7 + 3 * cfg->mhd : set_error(PB_EINVAL, "NULL cfg"); }
+extern "C" int pb_ncons(const pb_cfg_t *cfg) { return cfg ? 5 + 3 * cfg->mhd : set_error(PB_EINVAL, "NULL cfg"); }
+extern "C" long long pb_cells_per_block(const pb_cfg_t *cfg) { return cfg ? Lay(*cfg).ncell : set_error(PB_EINVAL, "NULL cfg"); }
 extern "C" int pb_device_sm_count(void) {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "cudaGetDevice");
@@ -132,7 +150,36 @@ struct ProfScope {
 namespace pb {
 static RedoQueue g_rq = {nullptr, nullptr, nullptr};
 static size_t g_rq_cap = 0;
-int redo_queue(size_t entries, RedoQueue &out) {
+// The library's work spaces (redo queue, con2prim scratch, error counter) are shared by all calls and used in stream
+// order: they belong to ONE device and to one stream at a time. workspace_claim() enforces that: a call from another
+// device, or on another stream while the previous stream still has work in flight, is refused (PB_EINVAL) instead of
+// racing on the queue counters. Streams that take part in one CUDA-graph capture count as one (the capture orders them).
+static int g_ws_device = -1;
+static cudaStream_t g_ws_stream = nullptr;
+static bool g_ws_have_stream = false;
+int workspace_claim(cudaStream_t s) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "cudaGetDevice");
+  if (g_ws_device >= 0 && dev != g_ws_device)
+    return set_error(PB_EINVAL, "phoebus_b200 work spaces belong to another device of this process (one process per GPU)");
+  g_ws_device = dev;
+  if (g_ws_have_stream && s != g_ws_stream) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      const cudaError_t q = cudaStreamQuery(g_ws_stream);
+      if (q == cudaErrorNotReady)
+        return set_error(PB_EINVAL, "phoebus_b200 work spaces are in use on another stream (one stage in flight at a time)");
+      if (q != cudaSuccess) cudaGetLastError(); // e.g. the old stream is being captured or was destroyed: not our business
+    }
+  }
+  g_ws_stream = s;
+  g_ws_have_stream = true;
+  return PB_OK;
+}
+int redo_queue(size_t entries, RedoQueue &out, cudaStream_t s) {
+  int rc = workspace_claim(s);
+  if (rc) return rc;
   if (!g_rq.count) {
     if (cudaMalloc(&g_rq.count, 2 * sizeof(unsigned) + sizeof(unsigned long long) + 8) != cudaSuccess)
       return set_cuda_error(cudaGetLastError(), "redo queue counters");
@@ -173,12 +220,14 @@ void prof_end(int id, cudaStream_t s) {
 
 extern "C" int pb_set_option(const char *key, int value) {
   if (key && !strcmp(key, "flux_split")) g_flux_split = value != 0;
+  else if (key && !strcmp(key, "flux_tma")) g_flux_tma = value != 0;
   else if (key && !strcmp(key, "c2p_arith") && value >= 0 && value <= 3) g_c2p_arith = value;
   else return set_error(PB_EINVAL, "pb_set_option: unknown key or value");
   return PB_OK;
 }
 extern "C" int pb_get_option(const char *key) {
   if (key && !strcmp(key, "flux_split")) return g_flux_split;
+  if (key && !strcmp(key, "flux_tma")) return g_flux_tma;
   if (key && !strcmp(key, "c2p_arith")) return g_c2p_arith;
   return set_error(PB_EINVAL, "pb_get_option: unknown key");
 }

@@ -186,7 +186,7 @@ extern "C" int pb_comm_allreduce_min(void *comm, double *value_dev, int n, void 
 // at run time, so one instantiated graph per (stage, container pair) serves every cycle.
 namespace pb {
 void set_stage_dt_pointer(const double *dt_dev); // update_kernels.cu
-int presize_workspaces(const pb_pack_t *pack, const pb_cfg_t *cfg); // zone_kernels.cu
+int presize_workspaces(const pb_pack_t *pack, const pb_cfg_t *cfg, cudaStream_t stream); // zone_kernels.cu
 }
 
 struct StageGraph {
@@ -202,7 +202,7 @@ extern "C" int pb_stage_graph_create(const pb_pack_t *pack, const pb_cfg_t *cfg,
   if (!graph_out || !dt_dev || !sc0 || !base || !sc1) return set_error(PB_EINVAL, "pb_stage_graph_create: NULL argument");
   if (comm && (rc = check_plan(plan, comm))) return rc;
   if (!stream) return set_error(PB_EINVAL, "pb_stage_graph_create: stream capture needs a non-default stream");
-  if ((rc = presize_workspaces(pack, cfg))) return rc; // no allocation may happen inside the capture
+  if ((rc = presize_workspaces(pack, cfg, (cudaStream_t)stream))) return rc; // no allocation may happen inside the capture
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
   if (e != cudaSuccess) return set_cuda_error(e, "cudaStreamBeginCapture");

@@ -7,10 +7,47 @@
 // reconstruction per cell and direction, as in the reference), hands its left-face state to the
 // neighbouring thread through shared memory, keeps its right-face state in registers and then solves
 // the Riemann problem at its own lower face. ql/qr never touch HBM.
+#include <cuda.h> // CUtensorMap and the enums of cuTensorMapEncodeTiled (types only: the entry point is fetched at run time)
+
+#include <cstdint>
+#include <cstring>
+
 #include "pb_device.cuh"
 #include "pb_host.hpp"
 
 namespace pb {
+
+// ---- TMA staging of the stencil tile (option flux_tma): the tile of one CTA is a dense 5-D box of the primitive slab
+// [block][component][k][j][i] — NP components x (NS + 4) cells along the stencil axis x TT pencils — so ONE
+// cp.async.bulk.tensor load issued by one thread replaces ~50 per-thread copies; completion is tracked by an mbarrier.
+PB_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+PB_DEV void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PB_DEV void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PB_DEV void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+PB_DEV void tma_load_5d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 
 // debugging switches: -DPB_FLUX_RECON_EXACT / -DPB_FLUX_RIEMANN_EXACT build the phase with the
 // compiler's own divide / sqrt expansion (same bits, slower)
@@ -30,6 +67,7 @@ struct FluxTile {
   int TT;      // pencils per CTA
   int nT1, nT; // transverse extents: fast one, total pencils per block
   int tiles;   // CTAs per block
+  int tiles1;  // TMA staging: tiles along the fast transverse axis (a tile is a box: it never wraps to the next row)
 };
 
 // ---- asynchronous global -> shared staging (LDGSTS): the copies bypass registers, so a CTA has its
@@ -48,10 +86,12 @@ constexpr int FLUX_NGEO = 19; // alpha, detgam, beta[3], gcov[10], gamma^{dd}, f
 //   s_ql  [NP][(NS+1)*TT]  left-face states handed to the neighbouring thread
 //   s_geo [FLUX_NGEO][NS*TT] this thread's face geometry + floor-table entries
 // 2 CTAs of <= 288 threads per SM: 96 registers (measured optimum on B200, profiles/r01_sweep2*)
-template <int DIR, int RECON, bool MHD>
-__global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const FluxTile ft) {
+template <int DIR, int RECON, bool MHD, bool TMA>
+__global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const FluxTile ft,
+                                                      const __grid_constant__ CUtensorMap tmap) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
-  extern __shared__ Real smem[];
+  extern __shared__ __align__(128) Real smem[];
+  __shared__ uint64_t s_bar;
   const Lay L(cfg);
   const int b = blockIdx.x / ft.tiles, tile = blockIdx.x % ft.tiles;
   const int NS = ft.NS, TT = ft.TT;
@@ -66,9 +106,17 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
     tI = tid % TT;
     sI = tid / TT;
   }
-  const int col = tile * TT + tI;
-  const bool valid = (col < ft.nT) && (sI < NS) && (tI < TT);
-  const int t1 = col % ft.nT1, t2 = col / ft.nT1;
+  int t1, t2;
+  bool valid;
+  if (TMA) { // rectangular tiles: TT pencils of one row
+    t1 = (tile % ft.tiles1) * TT + tI;
+    t2 = tile / ft.tiles1;
+    valid = (t1 < ft.nT1) && (sI < NS) && (tI < TT);
+  } else {
+    const int col = tile * TT + tI;
+    valid = (col < ft.nT) && (sI < NS) && (tI < TT);
+    t1 = col % ft.nT1, t2 = col / ft.nT1;
+  }
   int i, j, k, st;
   if (DIR == 1) {
     i = L.is - 1 + sI;
@@ -93,7 +141,19 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
   const int slot_r = (DIR == 1) ? tI * (NS + 1) + sI : sI * TT + tI;           // face s reads cell s-1's ql
   const int o = L.idx(k, j, i);
   const pb_block_t &blk = pack.blocks[b];
-  if (valid) {
+  if (TMA) {
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const int r0 = (tile % ft.tiles1) * TT, r1 = tile / ft.tiles1;
+      int c0, c1, c2;
+      if (DIR == 1) c0 = L.is - 3, c1 = L.js - L.dj + r0, c2 = L.ks - L.dk + r1;
+      else if (DIR == 2) c0 = L.is - 1 + r0, c1 = L.js - 3, c2 = L.ks - L.dk + r1;
+      else c0 = L.is - 1 + r0, c1 = L.js - 1 + r1, c2 = L.ks - 3;
+      mbar_expect_tx(&s_bar, (unsigned)(NP * plane_in * sizeof(Real)));
+      tma_load_5d(s_in, &tmap, &s_bar, c0, c1, c2, 0, b);
+    }
+  } else if (valid) {
     const Real *v = pack.prim + (size_t)b * NP * L.ncell + o;
 #pragma unroll
     for (int n = 0; n < NP; ++n) {
@@ -125,8 +185,12 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
     cp_async8(d + 17 * nthr, fp + L.ni);
   }
   cp_async_commit();
-  cp_async_wait<1>(); // the stencil tile has landed (the geometry may still be in flight)
-  __syncthreads();
+  if (TMA) {
+    mbar_wait(&s_bar, 0); // the box has landed (complete_tx)
+  } else {
+    cp_async_wait<1>(); // the stencil tile has landed (the geometry may still be in flight)
+    __syncthreads();
+  }
 
   Real qR[NP];
   if (valid) {
@@ -207,6 +271,29 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
   pack.fsig[((size_t)b * L.ndim + (DIR - 1)) * L.ncell + o] = speed;
 }
 
+// cuTensorMapEncodeTiled over the primitive slab as a 5-D tensor (i, j, k, component, block); the driver entry point is
+// resolved through the runtime (no link-time dependency on libcuda). Returns false if TMA cannot be used.
+static bool encode_prim_map(const pb_pack_t &pack, const pb_cfg_t &cfg, int nprim, const cuuint32_t box[5], CUtensorMap *out) {
+  typedef CUresult (*Encode)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                             const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode enc = [] {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+    return reinterpret_cast<Encode>(fn);
+  }();
+  if (!enc) return false;
+  const Lay L(cfg);
+  const cuuint64_t dims[5] = {(cuuint64_t)L.ni, (cuuint64_t)L.nj, (cuuint64_t)L.nk, (cuuint64_t)nprim, (cuuint64_t)pack.nblocks};
+  const cuuint64_t strides[4] = {(cuuint64_t)L.ni * 8, (cuuint64_t)L.ni * L.nj * 8, (cuuint64_t)L.ncell * 8, (cuuint64_t)nprim * L.ncell * 8};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(pack.prim) & 15) != 0) return false;
+  for (int d = 0; d < 5; ++d)
+    if (box[d] > 256 || box[d] > dims[d]) return false;
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, pack.prim, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int DIR, int RECON, bool MHD>
 static int launch_dir(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
   const Lay L(cfg);
@@ -233,15 +320,41 @@ static int launch_dir(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s
   if (ft.TT > ft.nT) ft.TT = ft.nT;
   while (ft.NS * ft.TT > 288 && ft.TT > 1) ft.TT--;
   if (ft.NS * ft.TT > 288) return set_error(PB_EINVAL, "block too large for the flux tile");
-  ft.tiles = (ft.nT + ft.TT - 1) / ft.TT;
+  // TMA staging needs a rectangular tile: TT pencils of ONE row (<= the row length, even along i for the 16-byte rule)
+  bool tma = flux_tma_enabled() && L.ni % 2 == 0;
+  int TTt = ft.TT > n1 ? n1 : ft.TT;
+  if (DIR == 1) tma = tma && (ft.NS + 4) % 2 == 0;
+  else {
+    TTt &= ~1;
+    tma = tma && TTt >= 2;
+  }
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof tmap);
+  if (tma) {
+    ft.TT = TTt;
+    const cuuint32_t S = (cuuint32_t)(ft.NS + 4), T = (cuuint32_t)ft.TT;
+    const cuuint32_t box[5] = {DIR == 1 ? S : T, DIR == 1 ? T : (DIR == 2 ? S : 1u), DIR == 3 ? S : 1u, (cuuint32_t)NC<MHD>::nprim, 1u};
+    tma = encode_prim_map(pack, cfg, NC<MHD>::nprim, box, &tmap);
+  }
+  ft.tiles1 = tma ? (n1 + ft.TT - 1) / ft.TT : 0;
+  ft.tiles = tma ? ft.tiles1 * n2 : (ft.nT + ft.TT - 1) / ft.TT;
   const int threads = ft.NS * ft.TT;
   const size_t smem = ((size_t)NC<MHD>::nprim * ((ft.NS + 1) + (ft.NS + 4)) * ft.TT + (size_t)FLUX_NGEO * threads) * sizeof(Real);
-  auto kern = flux_kernel<DIR, RECON, MHD>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_cuda_error(e, "flux smem attribute");
+  if (tma) {
+    auto kern = flux_kernel<DIR, RECON, MHD, true>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return set_cuda_error(e, "flux smem attribute");
+    }
+    kern<<<(unsigned)(pack.nblocks * ft.tiles), threads, smem, s>>>(pack, cfg, ft, tmap);
+  } else {
+    auto kern = flux_kernel<DIR, RECON, MHD, false>;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return set_cuda_error(e, "flux smem attribute");
+    }
+    kern<<<(unsigned)(pack.nblocks * ft.tiles), threads, smem, s>>>(pack, cfg, ft, tmap);
   }
-  kern<<<(unsigned)(pack.nblocks * ft.tiles), threads, smem, s>>>(pack, cfg, ft);
   return check_launch("flux_kernel");
 }
 

@@ -242,7 +242,7 @@ static int launch_dir_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStre
   if (rcode) return rcode;
   if (n2 >= (1ll << 32)) return set_error(PB_EINVAL, "pack too large for the 32-bit redo queue");
   RedoQueue rq;
-  if ((rcode = redo_queue((size_t)n2, rq))) return rcode;
+  if ((rcode = redo_queue((size_t)n2, rq, s))) return rcode;
   prof_begin(PB_TASK_RIEMANN, s);
   cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
   riemann_kernel<DIR, MHD><<<(unsigned)((n2 + PB_RIEMANN_T - 1) / PB_RIEMANN_T), PB_RIEMANN_T, 0, s>>>(pack, cfg, rf, ql, qr, rq);

@@ -413,6 +413,7 @@ extern "C" int pb_flux_ct(const pb_pack_t *pack, const pb_cfg_t *cfg, void *stre
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (!cfg->mhd || cfg->ndim == 1) return PB_OK; // ref: fluid.cpp:776-781
+  PB_NEED("pb_flux_ct", PB_F(pack, flux), PB_F(pack, emf));
   const Lay L(*cfg);
   const long long n = (long long)(cfg->nx[0] + 1) * (cfg->nx[1] + 1) * (cfg->ndim == 3 ? cfg->nx[2] + 1 : 1) * pack->nblocks;
   const int T = 256;
@@ -431,6 +432,7 @@ extern "C" int pb_fix_fluxes(const pb_pack_t *pack, const pb_cfg_t *cfg, void *s
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (!cfg->enable_flux_fixup) return PB_OK; // ref: fixup.cpp:734-736
+  PB_NEED("pb_fix_fluxes", PB_F(pack, flux));
   const int n1 = cfg->nx[0], n2 = cfg->ndim >= 2 ? cfg->nx[1] : 1, n3 = cfg->ndim >= 3 ? cfg->nx[2] : 1;
   int nface_max = n2 * n3;
   if (n1 * n3 > nface_max) nface_max = n1 * n3;
@@ -450,6 +452,8 @@ static long long n_interior(const pb_pack_t *pack, const pb_cfg_t *cfg) {
 extern "C" int pb_flux_divergence(const pb_pack_t *pack, const pb_cfg_t *cfg, double *dudt, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
+  if (!dudt) return set_error(PB_EINVAL, "pb_flux_divergence: NULL output");
+  PB_NEED("pb_flux_divergence", PB_F(pack, flux));
   const int T = 256;
   cudaStream_t s = (cudaStream_t)stream;
   if (cfg->mhd) divergence_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, dudt);
@@ -460,6 +464,7 @@ extern "C" int pb_flux_divergence(const pb_pack_t *pack, const pb_cfg_t *cfg, do
 extern "C" int pb_source_terms(const pb_pack_t *pack, const pb_cfg_t *cfg, double *gsrc, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
+  if (!gsrc) return set_error(PB_EINVAL, "pb_source_terms: NULL output");
   const int T = zone_threads();
   cudaStream_t s = (cudaStream_t)stream;
   if (cfg->mhd) source_kernel<true><<<grid_for(n_interior(pack, cfg), T), T, 0, s>>>(*pack, *cfg, gsrc);
@@ -718,6 +723,7 @@ extern "C" int pb_update_from_sources(const pb_pack_t *pack, const pb_cfg_t *cfg
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (!u0 || !ubase || !uout || !gsrc) return set_error(PB_EINVAL, "NULL container");
+  PB_NEED("pb_update_from_sources", PB_F(pack, flux));
   const int T = 256;
   cudaStream_t s = (cudaStream_t)stream;
   if (cfg->mhd)
@@ -738,6 +744,7 @@ extern "C" int pb_update_fused(const pb_pack_t *pack, const pb_cfg_t *cfg, const
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (!u0 || !ubase || !uout) return set_error(PB_EINVAL, "NULL conserved container");
+  PB_NEED("pb_update_fused", PB_F(pack, flux));
   const int T = zone_threads();
   cudaStream_t s = (cudaStream_t)stream;
   if (cfg->mhd)

@@ -751,6 +751,174 @@ __global__ void __launch_bounds__(128, 4) c2p_split_redo_kernel(const pb_pack_t 
   }
 }
 
+// ------------------------------------------------------------------ ConToPrim::Solve, one launch + warp-level parking
+// Option c2p_arith = 2 (the default): solve and unwrap in ONE kernel (measured faster than the three-launch split on the
+// torus, where the guess from the previous stage makes 1 - 3 regula-falsi iterations the norm and the unwrap + p2c tail is
+// the larger part), with the same warp-level handling of slowly converging zones: after every iteration the warp votes,
+// and once at most PB_C2P_DEFER lanes are still iterating (after >= PB_C2P_DEFER_IT iterations) those lanes park their
+// bracket state; c2p_finish_kernel resumes them, 32 slow zones per warp, and unwraps them. Zones the fast arithmetic
+// rejects go to the redo queue as before.
+template <bool MHD>
+PB_DEV void c2p_store_zone(const pb_cfg_t &cfg, const FloorCtx &fc, const PointGeom &g, const ZonePtr<MHD> &z, const Lay &L, int b, int o,
+                           const Real *U, const Real *U0, const Real *P, Real temp, Real mu, const Real sig[3], bool ok, unsigned char *zflags) {
+  constexpr int NP = NC<MHD>::nprim;
+  store_comps<NP>(z.prim, z.ncell, P);
+  *z.temp = temp;
+  *z.mu = mu;
+  for (int a = 0; a < L.ndim; ++a) z.csig[(size_t)a * z.ncell] = sig[a];
+  bool changed = false;
+#pragma unroll
+  for (int n = 0; n < 5; ++n) changed = changed || U[n] != U0[n] || isnan(U[n]);
+  if (changed) {
+#pragma unroll
+    for (int n = 0; n < 5; ++n) z.cons[(size_t)n * z.ncell] = U[n];
+  }
+  *z.fail = ok ? 1.0 : 0.0;
+  if (zflags) {
+    unsigned char f = ok ? 0 : ZF_FAIL;
+    if (cfg.enable_floors && floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_FLOOR;
+    zflags[(size_t)b * L.ncell + o] = f;
+  }
+}
+
+template <bool MHD>
+__global__ void __launch_bounds__(128, PB_C2P_MINB) c2p_park_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const C2PWork work,
+                                                                    unsigned long long *err_count, unsigned char *zflags, const RedoQueue rq,
+                                                                    const C2PWorkspace ws) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  __shared__ unsigned s_stat[C2P_NSTAT];
+  stats_begin(s_stat);
+  const Lay L(cfg);
+  int b, k, j, i;
+  if (c2p_zone_of_thread(work, L, b, k, j, i)) {
+    const unsigned lanes = __activemask(); // the lanes of this warp that own a zone
+    const int o = L.idx(k, j, i);
+    const unsigned zone = (unsigned)((long long)b * L.ncell + o);
+    const pb_block_t &blk = pack.blocks[b];
+    const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+    PointGeom g;
+    g.load(gt, 0, gt.cell(k, j, i));
+    const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+    const ZonePtr<MHD> z(pack, cons, L, b, o);
+    Real U[NCn], U0[5], P[NP];
+    load_comps<NCn>(z.cons, L.ncell, U);
+#pragma unroll
+    for (int n = 0; n < 5; ++n) U0[n] = U[n];
+    const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
+    ArithFast af;
+    C2PVars<MHD> s;
+    c2p_setup<MHD>(af, cfg, fc, g, U, s);
+    Residual<ArithFast> res = c2p_residual<MHD>(af, cfg, fc, s);
+    RFState st;
+    const bool bracketed = rf_begin(af, res, 0.0, 1.0, *z.mu, st);
+    bool active = !nan_in && bracketed && rf_running(st, cfg.c2p_tol, cfg.c2p_max_iter);
+    bool parked = false;
+    while (__any_sync(lanes, active)) {
+      if (active) {
+        rf_iterate(af, res, st);
+        active = rf_running(st, cfg.c2p_tol, cfg.c2p_max_iter);
+      }
+      const int nact = __popc(__ballot_sync(lanes, active));
+      if (nact > 0 && nact <= PB_C2P_DEFER && st.it >= PB_C2P_DEFER_IT && active && !af.failed()) {
+        const unsigned e = atomicAdd(ws.slow_count, 1u);
+        if (e < ws.slow_cap) {
+          SlowEntry &q = ws.slow[e];
+          q.zone = zone;
+          q.it = st.it, q.b1 = st.b1, q.b2 = st.b2;
+          q.a = st.a, q.b = st.b, q.ya = st.ya, q.yb = st.yb, q.sign = st.sign;
+          parked = true;
+          active = false;
+        }
+      }
+    }
+    if (parked) {
+      if (ws.stats) atomicAdd(&s_stat[34], 1u);
+    } else if (nan_in) { // the NaN guard: nothing but the failure flag is written (ref: con2prim_robust.hpp:318-324)
+      *z.fail = 0.0;
+      if (zflags) {
+        load_comps<NP>(z.prim, L.ncell, P);
+        zflags[(size_t)b * L.ncell + o] = ZF_FAIL | ((cfg.enable_floors && floors_needed<MHD>(cfg, fc, g, P)) ? ZF_FLOOR : 0);
+      }
+      if (ws.stats) atomicAdd(&s_stat[33], 1u);
+    } else if (!bracketed && !af.failed()) { // the reference aborts here; p.bfield is all it has written by then
+      if (MHD) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) z.prim[(size_t)(PB_ + a) * z.ncell] = s.Bp[a];
+      }
+      if (err_count) atomicAdd(err_count, 1ULL);
+      *z.fail = 0.0;
+      if (zflags) {
+        load_comps<NP>(z.prim, L.ncell, P);
+        zflags[(size_t)b * L.ncell + o] = ZF_FAIL | ((cfg.enable_floors && floors_needed<MHD>(cfg, fc, g, P)) ? ZF_FLOOR : 0);
+      }
+      if (ws.stats) atomicAdd(&s_stat[33], 1u);
+    } else {
+      const Real mu = 0.5 * (st.a + st.b);
+      Real temp, sig[3];
+      const bool ok = c2p_unwrap<MHD>(af, cfg, g, s, res, mu, U, P, temp, sig);
+      if (af.failed()) {
+        rq.list[atomicAdd(rq.count, 1u)] = zone; // nothing stored: c2p_redo_kernel solves the zone with the compiler's divide / sqrt
+      } else {
+        c2p_store_zone<MHD>(cfg, fc, g, z, L, b, o, U, U0, P, temp, mu, sig, ok, zflags);
+        if (ws.stats) {
+          atomicAdd(&s_stat[st.it < 31 ? st.it : 31], 1u);
+          atomicAdd(&s_stat[35], 1u);
+          if (res.used_bounds()) atomicAdd(&s_stat[32], 1u);
+          if (!ok) atomicAdd(&s_stat[33], 1u);
+        }
+      }
+    }
+  }
+  stats_end(s_stat, ws.stats);
+}
+
+// the parked zones of c2p_park_kernel: resume the root find from the saved bracket, unwrap, store
+template <bool MHD>
+__global__ void __launch_bounds__(128, PB_C2P_MINB) c2p_finish_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, unsigned char *zflags,
+                                                                      const RedoQueue rq, const C2PWorkspace ws) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  const Lay L(cfg);
+  unsigned n = *ws.slow_count;
+  if (n > ws.slow_cap) n = ws.slow_cap;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const SlowEntry q = ws.slow[e];
+    const int b = (int)(q.zone / (unsigned)L.ncell), o = (int)(q.zone % (unsigned)L.ncell);
+    const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
+    const pb_block_t &blk = pack.blocks[b];
+    const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+    PointGeom g;
+    g.load(gt, 0, gt.cell(k, j, i));
+    const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+    const ZonePtr<MHD> z(pack, cons, L, b, o);
+    Real U[NCn], U0[5], P[NP];
+    load_comps<NCn>(z.cons, L.ncell, U);
+#pragma unroll
+    for (int m = 0; m < 5; ++m) U0[m] = U[m];
+    ArithFast af;
+    C2PVars<MHD> s;
+    c2p_setup<MHD>(af, cfg, fc, g, U, s);
+    Residual<ArithFast> res = c2p_residual<MHD>(af, cfg, fc, s);
+    RFState st;
+    st.a = q.a, st.b = q.b, st.ya = q.ya, st.yb = q.yb, st.sign = q.sign;
+    st.it = q.it, st.b1 = q.b1, st.b2 = q.b2;
+    while (rf_running(st, cfg.c2p_tol, cfg.c2p_max_iter)) rf_iterate(af, res, st);
+    const Real mu = 0.5 * (st.a + st.b);
+    Real temp, sig[3];
+    const bool ok = c2p_unwrap<MHD>(af, cfg, g, s, res, mu, U, P, temp, sig);
+    if (af.failed()) {
+      rq.list[atomicAdd(rq.count, 1u)] = q.zone;
+    } else {
+      c2p_store_zone<MHD>(cfg, fc, g, z, L, b, o, U, U0, P, temp, mu, sig, ok, zflags);
+      if (ws.stats) {
+        atomicAdd(&ws.stats[st.it < 31 ? st.it : 31], 1ULL);
+        atomicAdd(&ws.stats[35], 1ULL);
+        if (res.used_bounds()) atomicAdd(&ws.stats[32], 1ULL);
+        if (!ok) atomicAdd(&ws.stats[33], 1ULL);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ ConToPrim::Solve fixup
 // MODE 0: the task as the reference runs it (every interior zone reads its fail flag).
 // MODE 1 / 2: driven by the zone flags (post-c2p pass / stale-prim pass of region 7); the zone's
@@ -1177,11 +1345,11 @@ static int c2p_workspace(size_t cells, size_t nthr, C2PWorkspace &out) {
   return PB_OK;
 }
 // everything the sequencer allocates lazily, sized for this pack up front (CUDA-graph capture may not allocate)
-int presize_workspaces(const pb_pack_t *pack, const pb_cfg_t *cfg) {
+int presize_workspaces(const pb_pack_t *pack, const pb_cfg_t *cfg, cudaStream_t stream) {
   const Lay L(*cfg);
   const size_t cells = (size_t)pack->nblocks * L.ncell;
   RedoQueue rq;
-  int rc = redo_queue(cells, rq);
+  int rc = redo_queue(cells, rq, stream);
   if (rc) return rc;
   C2PWorkspace ws;
   if ((rc = c2p_workspace(cells, cells, ws))) return rc;
@@ -1200,13 +1368,13 @@ static int launch_c2p_work(const pb_pack_t *pack, const pb_cfg_t *cfg, double *c
   RedoQueue rq{nullptr, nullptr, nullptr};
   if (mode == 2) {
     if ((long long)pack->nblocks * Lay(*cfg).ncell >= (1ll << 32)) return set_error(PB_EINVAL, "pack too large for the 32-bit redo queue");
-    int rc = redo_queue((size_t)nthr, rq);
+    int rc = redo_queue((size_t)nthr, rq, s);
     if (rc) return rc;
     cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
   }
   if (mode == 3) {
     if ((long long)pack->nblocks * Lay(*cfg).ncell >= (1ll << 31)) return set_error(PB_EINVAL, "pack too large for the 31-bit redo queue");
-    int rc = redo_queue((size_t)nthr, rq);
+    int rc = redo_queue((size_t)nthr, rq, s);
     if (rc) return rc;
     C2PWorkspace ws;
     if ((rc = c2p_workspace((size_t)pack->nblocks * Lay(*cfg).ncell, (size_t)nthr, ws))) return rc;
@@ -1225,6 +1393,26 @@ static int launch_c2p_work(const pb_pack_t *pack, const pb_cfg_t *cfg, double *c
       c2p_split_redo_kernel<false><<<nsm * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq, ws.stats);
     }
     return check_launch("c2p_solve_kernel");
+  }
+  if (mode == 2) {
+    if ((long long)pack->nblocks * Lay(*cfg).ncell >= (1ll << 32)) return set_error(PB_EINVAL, "pack too large for the 32-bit redo queue");
+    int rc = redo_queue((size_t)nthr, rq, s);
+    if (rc) return rc;
+    C2PWorkspace ws;
+    if ((rc = c2p_workspace((size_t)pack->nblocks * Lay(*cfg).ncell, (size_t)nthr, ws))) return rc;
+    cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
+    cudaMemsetAsync(ws.slow_count, 0, sizeof(unsigned), s);
+    const int nsm = sm_count();
+    if (cfg->mhd) {
+      c2p_park_kernel<true><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, err_counter(), zflags, rq, ws);
+      c2p_finish_kernel<true><<<nsm * 2, T, 0, s>>>(*pack, *cfg, cons, zflags, rq, ws);
+      c2p_redo_kernel<true><<<nsm * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq);
+    } else {
+      c2p_park_kernel<false><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, err_counter(), zflags, rq, ws);
+      c2p_finish_kernel<false><<<nsm * 2, T, 0, s>>>(*pack, *cfg, cons, zflags, rq, ws);
+      c2p_redo_kernel<false><<<nsm * 4, 128, 0, s>>>(*pack, *cfg, cons, err_counter(), zflags, rq);
+    }
+    return check_launch("c2p_park_kernel");
   }
 #define PB_C2P(M, A) c2p_kernel<M, A><<<grid, T, 0, s>>>(*pack, *cfg, cons, work, err_counter(), zflags, rq)
   if (cfg->mhd) {
@@ -1318,12 +1506,15 @@ extern "C" int pb_cons_to_prim(const pb_pack_t *pack, const pb_cfg_t *cfg, doubl
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (!cons) return set_error(PB_EINVAL, "cons is NULL");
+  PB_NEED("pb_cons_to_prim", PB_F(pack, temp), PB_F(pack, c2p_mu), PB_F(pack, fail), PB_F(pack, csig));
   return launch_c2p(pack, cfg, cons, ib, jb, kb, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int pb_c2p_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
+  if (!cons) return set_error(PB_EINVAL, "cons is NULL");
+  PB_NEED("pb_c2p_fixup", PB_F(pack, temp), PB_F(pack, fail), PB_F(pack, csig));
   return launch_fixup(pack, cfg, cons, 0, nullptr, (cudaStream_t)stream);
 }
 
@@ -1331,6 +1522,8 @@ extern "C" int pb_apply_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, doubl
                                unsigned long long *counters, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
+  if (!cons) return set_error(PB_EINVAL, "cons is NULL");
+  PB_NEED("pb_apply_floors", PB_F(pack, temp), PB_F(pack, c2p_mu), PB_F(pack, csig));
   return launch_floors(pack, cfg, cons, counters, 0, nullptr, nullptr, nullptr, 1.0, (cudaStream_t)stream);
 }
 
@@ -1352,6 +1545,8 @@ extern "C" int pb_prim_to_cons(const pb_pack_t *pack, const pb_cfg_t *cfg, doubl
                                const int jb[2], const int kb[2], void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
+  if (!cons) return set_error(PB_EINVAL, "cons is NULL");
+  PB_NEED("pb_prim_to_cons", PB_F(pack, csig));
   const Region reg{ib[0], ib[1], jb[0], jb[1], kb[0], kb[1]};
   if (reg.n() <= 0) return PB_OK;
   const int T = zone_threads();
@@ -1370,6 +1565,7 @@ extern "C" int pb_apply_bcs_ex(const pb_pack_t *pack, const pb_cfg_t *cfg, doubl
   int rc = check_args(pack, cfg);
   if (rc) return rc;
   if (!cons || (what & 3) == 0) return set_error(PB_EINVAL, "pb_apply_bcs_ex: NULL container or empty task mask");
+  PB_NEED("pb_apply_bcs", PB_F(pack, temp), PB_F(pack, c2p_mu), PB_F(pack, fail), PB_F(pack, csig));
   const Lay L(*cfg);
   const Shell sh(L);
   const int nlist = pack->bc_blocks ? pack->n_bc_blocks : pack->nblocks;
@@ -1386,6 +1582,8 @@ extern "C" int pb_estimate_dt(const pb_pack_t *pack, const pb_cfg_t *cfg, int ha
                               void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
+  if (!dt_out) return set_error(PB_EINVAL, "pb_estimate_dt: NULL output");
+  PB_NEED("pb_estimate_dt", PB_F(pack, csig), PB_F(pack, fsig));
   const Lay L(*cfg);
   const Region reg = interior(L);
   const int T = 256;
@@ -1409,4 +1607,16 @@ extern "C" int pb_c2p_stats(int enable, unsigned long long out_host[36]) {
   if (enable && !g_c2p_stats_on) cudaMemset(g_c2p_stats, 0, 36 * sizeof(unsigned long long));
   g_c2p_stats_on = enable != 0;
   return PB_OK;
+}
+
+// Unbracketed con2prim roots since the library was loaded (or since the last reset): the reference aborts the run there
+// (PARTHENON_FAIL, ref: src/phoebus_utils/root_find.hpp:115-118); here the zone is marked failed and counted, and the
+// host layer decides (phoebus_b200.driver raises). Synchronises the device.
+extern "C" long long pb_c2p_unbracketed_count(int reset) {
+  unsigned long long *c = err_counter();
+  if (!c) return set_cuda_error(cudaGetLastError(), "pb_c2p_unbracketed_count");
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, c, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "pb_c2p_unbracketed_count");
+  if (reset) cudaMemset(c, 0, sizeof v);
+  return (long long)v;
 }

@@ -196,7 +196,7 @@ class FluidDriver:
         split = m.recon_lr is not None and self.L.pb_get_option(b"flux_split") == 1
         # flux: recon + riemann + riemann_redo per direction (split) or one fused launch; update; fixup; floors...
         n = m.ndim * (3 if split else 1) + 1 + 1 + 1 + 1
-        kc = {0: 1, 1: 1, 2: 2, 3: 4}[self.L.pb_get_option(b"c2p_arith")]  # kernels per con2prim task (solve, slow, unwrap, redo)
+        kc = {0: 1, 1: 1, 2: 3, 3: 4}[self.L.pb_get_option(b"c2p_arith")]  # kernels per con2prim task (solve, slow, unwrap, redo)
         n += kc - 1
         if m.gsrc is not None:
             n += 1
