@@ -337,6 +337,11 @@ int pb_profile_read(double ms[PB_NTASK], int calls[PB_NTASK]);
 
 /* Run-time options of the library (initial values from the environment variables in parentheses):
  *   "flux_split" 1|0  (PB_FLUX_MODE=split|fused)  two-launch flux path when the pack has recon_lr, else the fused kernel
+ *   "riemann_blocks" 1|0 (PB_RIEMANN_BLOCKS=1|0) two Riemann launches per direction: MeshBlocks whose face states carry no
+ *                magnetic field (flagged by the reconstruction) go through the exact unmagnetised variant at a higher
+ *                occupancy, the others through the general kernel; 0: one launch, variant chosen per warp
+ *   "flag_compact" 1|0 (PB_FLAG_PASS=compact|packed) the flag-driven fixup / floor passes compact the flagged zones into a
+ *                queue and handle one zone per thread (default), or walk 16 flags per thread serially
  *   "flux_tma"   1|0  (PB_FLUX_STAGE=tma|cpasync) the fused flux kernel stages its stencil tile with one TMA tensor load
  *                (cp.async.bulk.tensor, 5-D box of the primitive slab) per CTA, or with per-thread cp.async copies
  *   "c2p_arith"  2|3|0|1 (PB_C2P_ARITH=queue|split|exact|inline) con2prim: one launch with warp-level parking of slowly

@@ -83,6 +83,16 @@ static int g_flux_tma = [] {
   const char *e = getenv("PB_FLUX_STAGE");
   return (e && e[0] == 'c') ? 0 : 1; // cpasync | tma (default)
 }();
+static int g_flag_compact = [] {
+  const char *e = getenv("PB_FLAG_PASS");
+  return (e && e[0] == 'p') ? 0 : 1; // packed (16 zones per thread, serial) | compact (queue, one zone per thread; default)
+}();
+bool flag_compaction_enabled() { return g_flag_compact != 0; }
+static int g_riemann_blocks = [] {
+  const char *e = getenv("PB_RIEMANN_BLOCKS");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+bool riemann_block_split_enabled() { return g_riemann_blocks != 0; }
 bool flux_split_enabled() { return g_flux_split != 0; }
 bool flux_tma_enabled() { return g_flux_tma != 0; }
 int c2p_arith_mode() { return g_c2p_arith; }
@@ -221,6 +231,8 @@ void prof_end(int id, cudaStream_t s) {
 extern "C" int pb_set_option(const char *key, int value) {
   if (key && !strcmp(key, "flux_split")) g_flux_split = value != 0;
   else if (key && !strcmp(key, "flux_tma")) g_flux_tma = value != 0;
+  else if (key && !strcmp(key, "flag_compact")) g_flag_compact = value != 0;
+  else if (key && !strcmp(key, "riemann_blocks")) g_riemann_blocks = value != 0;
   else if (key && !strcmp(key, "c2p_arith") && value >= 0 && value <= 3) g_c2p_arith = value;
   else return set_error(PB_EINVAL, "pb_set_option: unknown key or value");
   return PB_OK;
@@ -228,6 +240,8 @@ extern "C" int pb_set_option(const char *key, int value) {
 extern "C" int pb_get_option(const char *key) {
   if (key && !strcmp(key, "flux_split")) return g_flux_split;
   if (key && !strcmp(key, "flux_tma")) return g_flux_tma;
+  if (key && !strcmp(key, "flag_compact")) return g_flag_compact;
+  if (key && !strcmp(key, "riemann_blocks")) return g_riemann_blocks;
   if (key && !strcmp(key, "c2p_arith")) return g_c2p_arith;
   return set_error(PB_EINVAL, "pb_get_option: unknown key");
 }

@@ -17,6 +17,20 @@ namespace pb {
 __device__ unsigned g_diag = 0;
 #endif
 
+// one int per MeshBlock, library-owned: "this direction's face states of the block carry a non-zero B"
+static int *g_bflag = nullptr;
+static int g_bflag_cap = 0;
+static int *block_flags(int nblocks) {
+  if (nblocks > g_bflag_cap) {
+    cudaDeviceSynchronize();
+    if (g_bflag) cudaFree(g_bflag);
+    g_bflag = nullptr;
+    if (cudaMalloc(&g_bflag, sizeof(int) * (size_t)nblocks) != cudaSuccess) return nullptr;
+    g_bflag_cap = nblocks;
+  }
+  return g_bflag;
+}
+
 struct Box { // inclusive cell ranges of one block
   int i0, i1, j0, j1, k0, k1;
   __host__ __device__ int ni() const { return i1 - i0 + 1; }
@@ -62,10 +76,12 @@ template <int RECON> PB_DEV void load_stencil(const Real *p, int st, Real q[5]) 
   q[4] = RECON >= 2 ? __ldg(p + 2 * st) : q[2];
 }
 
+// bflag (may be NULL; MHD packs only): bflag[b] is set when the block gets a face state with a non-zero B component, i.e. when
+// the Riemann solve of this direction cannot take the unmagnetised variant for the whole block
 template <int DIR, int RECON, int NP>
 __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const Real *__restrict__ prim, Real *__restrict__ ql,
                                                                    Real *__restrict__ qr, const pb_cfg_t cfg, const Box reg,
-                                                                   const int nblocks) {
+                                                                   const int nblocks, int *__restrict__ bflag) {
   const Lay L(cfg);
   int b, k, j, i;
   if (!cell_of_thread(reg, nblocks, b, k, j, i)) return;
@@ -75,6 +91,7 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
   Real *l = ql + o + st; // my left state belongs to the face of cell s+1
   Real *r = qr + o;
   ArithFast af;
+  long long anyB = 0;
 #pragma unroll
   for (int n = 0; n < NP; ++n) {
     const Real *p = v + (size_t)n * L.ncell;
@@ -84,7 +101,9 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
     recon5z<RECON>(af, q[0], q[1], q[2], q[3], q[4], a, c);
     l[(size_t)n * L.ncell] = a;
     r[(size_t)n * L.ncell] = c;
+    if (NP == 10 && n >= PB_ && n < PB_ + 3) anyB |= __double_as_longlong(a) | __double_as_longlong(c);
   }
+  if (NP == 10 && bflag && (anyB << 1) != 0) bflag[b] = 1; // (racing stores of the same value)
   if (af.failed()) { // operands outside the fast divide's range: redo with the compiler's a/b
     ArithExact ax;
 #pragma unroll 1
@@ -96,6 +115,7 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
       recon5z<RECON>(ax, q[0], q[1], q[2], q[3], q[4], a, c);
       l[(size_t)n * L.ncell] = a;
       r[(size_t)n * L.ncell] = c;
+      if (NP == 10 && bflag && n >= PB_ && n < PB_ + 3 && ((__double_as_longlong(a) | __double_as_longlong(c)) << 1) != 0) bflag[b] = 1;
     }
   }
 }
@@ -105,7 +125,8 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
 #ifndef PB_RIEMANN_BZ
 #define PB_RIEMANN_BZ 1
 #endif
-template <int DIR, bool MHD, class AR, bool BZFAST = (PB_RIEMANN_BZ != 0)>
+// BMODE: 0 = decide per warp from the loaded states, 1 = the caller knows that B == 0 (whole block), 2 = general path only
+template <int DIR, bool MHD, class AR, int BMODE = (PB_RIEMANN_BZ != 0 ? 0 : 2)>
 PB_DEV bool riemann_face(const pb_pack_t &pack, const pb_cfg_t &cfg, const Lay &L, const Real *__restrict__ ql,
                          const Real *__restrict__ qr, int b, int k, int j, int i) {
   constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
@@ -142,17 +163,17 @@ PB_DEV bool riemann_face(const pb_pack_t &pack, const pb_cfg_t &cfg, const Lay &
   AR ar;
   // unmagnetised faces (both states have B == +-0 in all components) take the exact hydrodynamic variant of
   // prim_to_flux; the decision is made per warp so that the two code paths never run side by side
-  bool bzero = false;
-  if (MHD && BZFAST) {
+  bool bzero = MHD && BMODE == 1;
+  if (MHD && BMODE == 0) {
     long long any = 0;
 #pragma unroll
     for (int m = 0; m < 3; ++m) any |= __double_as_longlong(qL[PB_ + m]) | __double_as_longlong(qR[PB_ + m]);
     bzero = __all_sync(__activemask(), (any << 1) == 0);
   }
-  if (bzero) {
+  if (MHD && BMODE != 2 && bzero) {
     prim_to_flux<DIR, MHD, true>(ar, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
     prim_to_flux<DIR, MHD, true>(ar, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
-  } else {
+  } else if (BMODE != 1 || !MHD) {
     prim_to_flux<DIR, MHD, false>(ar, cfg, fc, g, gdd, qL, vml, vpl, Ul, Fl);
     prim_to_flux<DIR, MHD, false>(ar, cfg, fc, g, gdd, qR, vmr, vpr, Ur, Fr);
   }
@@ -193,16 +214,30 @@ PB_DEV void face_of_index(const Box &r, long long t, int &b, int &k, int &j, int
   k = r.k0 + q2;
 }
 
-template <int DIR, bool MHD>
-__global__ void __launch_bounds__(PB_RIEMANN_T, PB_RIEMANN_MINB) riemann_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Box reg,
-                                                                       const Real *__restrict__ ql, const Real *__restrict__ qr,
-                                                                       const RedoQueue rq) {
+// bflag == NULL: every face, unmagnetised variant chosen per warp. bflag != NULL: the kernel is launched twice over the same
+// faces — WANT = 0 takes the MeshBlocks without any non-zero B face state (flag written by recon_kernel) through the
+// unmagnetised variant only, compiled for a higher occupancy; WANT = 1 takes the others through the per-warp decision.
+#ifndef PB_RIEMANN_BZ_MINB
+#define PB_RIEMANN_BZ_MINB 5
+#endif
+template <int DIR, bool MHD, int WANT>
+__global__ void __launch_bounds__(PB_RIEMANN_T, (WANT == 0 ? PB_RIEMANN_BZ_MINB : PB_RIEMANN_MINB))
+    riemann_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Box reg, const Real *__restrict__ ql, const Real *__restrict__ qr,
+                   const RedoQueue rq, const int *__restrict__ bflag) {
   const Lay L(cfg);
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= reg.n() * pack.nblocks) return;
   int b, k, j, i;
   face_of_index(reg, t, b, k, j, i);
-  if (riemann_face<DIR, MHD, ArithFast>(pack, cfg, L, ql, qr, b, k, j, i)) rq.list[atomicAdd(rq.count, 1u)] = (unsigned)t;
+  bool bad;
+  if (WANT == 0) {
+    if (__ldg(bflag + b) != 0) return;
+    bad = riemann_face<DIR, MHD, ArithFast, 1>(pack, cfg, L, ql, qr, b, k, j, i);
+  } else {
+    if (bflag && __ldg(bflag + b) == 0) return;
+    bad = riemann_face<DIR, MHD, ArithFast>(pack, cfg, L, ql, qr, b, k, j, i);
+  }
+  if (bad) rq.list[atomicAdd(rq.count, 1u)] = (unsigned)t;
 }
 
 template <int DIR, bool MHD>
@@ -215,7 +250,7 @@ __global__ void __launch_bounds__(128) riemann_redo_kernel(const pb_pack_t pack,
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     int b, k, j, i;
     face_of_index(reg, (long long)rq.list[e], b, k, j, i);
-    riemann_face<DIR, MHD, ArithExact, false>(pack, cfg, L, ql, qr, b, k, j, i);
+    riemann_face<DIR, MHD, ArithExact, 2>(pack, cfg, L, ql, qr, b, k, j, i);
   }
 }
 
@@ -235,8 +270,13 @@ static int launch_dir_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStre
   else rf.k0 += 1;
   Real *ql = pack.recon_lr, *qr = pack.recon_lr + (size_t)pack.nblocks * NP * L.ncell;
   const long long n1 = rc.n() * pack.nblocks, n2 = rf.n() * pack.nblocks;
+  int *bflag = nullptr;
+  if (MHD && riemann_block_split_enabled()) {
+    if (!(bflag = block_flags(pack.nblocks))) return set_cuda_error(cudaGetLastError(), "block flags");
+    cudaMemsetAsync(bflag, 0, sizeof(int) * pack.nblocks, s);
+  }
   prof_begin(PB_TASK_RECON, s);
-  recon_kernel<DIR, RECON, NP><<<(unsigned)((n1 + PB_RECON_T - 1) / PB_RECON_T), PB_RECON_T, 0, s>>>(pack.prim, ql, qr, cfg, rc, pack.nblocks);
+  recon_kernel<DIR, RECON, NP><<<(unsigned)((n1 + PB_RECON_T - 1) / PB_RECON_T), PB_RECON_T, 0, s>>>(pack.prim, ql, qr, cfg, rc, pack.nblocks, bflag);
   prof_end(PB_TASK_RECON, s);
   int rcode = check_launch("recon_kernel");
   if (rcode) return rcode;
@@ -245,8 +285,10 @@ static int launch_dir_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStre
   if ((rcode = redo_queue((size_t)n2, rq, s))) return rcode;
   prof_begin(PB_TASK_RIEMANN, s);
   cudaMemsetAsync(rq.count, 0, sizeof(unsigned), s);
-  riemann_kernel<DIR, MHD><<<(unsigned)((n2 + PB_RIEMANN_T - 1) / PB_RIEMANN_T), PB_RIEMANN_T, 0, s>>>(pack, cfg, rf, ql, qr, rq);
-  riemann_redo_kernel<DIR, MHD><<<148 * 4, 128, 0, s>>>(pack, cfg, rf, ql, qr, rq);
+  const unsigned gr = (unsigned)((n2 + PB_RIEMANN_T - 1) / PB_RIEMANN_T);
+  if (bflag) riemann_kernel<DIR, MHD, 0><<<gr, PB_RIEMANN_T, 0, s>>>(pack, cfg, rf, ql, qr, rq, bflag);
+  riemann_kernel<DIR, MHD, 1><<<gr, PB_RIEMANN_T, 0, s>>>(pack, cfg, rf, ql, qr, rq, bflag);
+  riemann_redo_kernel<DIR, MHD><<<sm_count() * 4, 128, 0, s>>>(pack, cfg, rf, ql, qr, rq);
   prof_end(PB_TASK_RIEMANN, s);
   return check_launch("riemann_kernel");
 }
@@ -266,6 +308,8 @@ template <bool MHD> static int launch_recon_split(const pb_pack_t &pack, const p
   }
   return set_error(PB_EINVAL, "unknown reconstruction");
 }
+
+int presize_block_flags(int nblocks) { return block_flags(nblocks) ? PB_OK : set_cuda_error(cudaGetLastError(), "block flags"); }
 
 int calculate_fluxes_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s) {
   return cfg.mhd ? launch_recon_split<true>(pack, cfg, s) : launch_recon_split<false>(pack, cfg, s);

@@ -28,6 +28,8 @@ int need_fields(const char *entry, std::initializer_list<std::pair<const void *,
 // tunables (environment overrides, read once): PB_FLUX_THREADS, PB_ZONE_THREADS
 int flux_threads_target();
 int zone_threads();
+bool riemann_block_split_enabled(); // option riemann_blocks / PB_RIEMANN_BLOCKS=1|0: unmagnetised MeshBlocks get their own Riemann launch
+bool flag_compaction_enabled(); // option flag_compact / PB_FLAG_PASS=compact|packed: flag-driven fixup / floor passes
 bool flux_tma_enabled();   // option flux_tma / PB_FLUX_STAGE=tma|cpasync: how the fused flux kernel stages its stencil tile
 bool flux_split_enabled(); // option flux_split / PB_FLUX_MODE=fused|split (default split when the pack carries ql/qr scratch)
 int c2p_arith_mode();      // option c2p_arith / PB_C2P_ARITH: 0 exact, 1 inline, 2 one launch + parking + redo queue (default), 3 split

@@ -465,7 +465,7 @@ struct C2PWorkspace {
 #define PB_C2P_DEFER 4 // park when at most this many lanes of the warp are still iterating ...
 #endif
 #ifndef PB_C2P_DEFER_IT
-#define PB_C2P_DEFER_IT 3 // ... and they have done at least this many iterations (1 - 3 iterations are the norm, measured)
+#define PB_C2P_DEFER_IT 4 // ... and they have done at least this many iterations (1 - 3 iterations are the norm, measured)
 #endif
 // statistics are summed per CTA in shared memory and flushed with one atomic per non-empty counter
 constexpr int C2P_NSTAT = 36;
@@ -1056,6 +1056,69 @@ __global__ void __launch_bounds__(128, 4) floors_packed_kernel(const pb_pack_t p
   }
 }
 
+// Compaction of the flagged zones (the general case: a run where a large share of the domain floors every stage would
+// make the 16-zones-per-thread walk above serial): one pass over the flag bytes appends the linear index of every flagged
+// zone to a device queue (16 flags per thread, one atomic per warp), then floors_queue_kernel / fixup_queue_kernel handle
+// ONE zone per thread from the queue — the cost of the pass is that of con2prim over the same number of zones.
+__global__ void __launch_bounds__(256) flag_compact_kernel(const unsigned char *zflags, long long nvec_total, unsigned char bit,
+                                                           const RedoQueue q) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned mask = 0;
+  if (t < nvec_total) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(zflags) + t);
+    const unsigned rep = 0x01010101u * bit;
+    if (((w.x | w.y | w.z | w.w) & rep) != 0) {
+      const unsigned words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if ((words[qq] >> (8 * c)) & bit) mask |= 1u << (4 * qq + c);
+    }
+  }
+  const int mine = __popc(mask);
+  int incl = mine; // inclusive prefix sum over the warp
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  unsigned base = 0;
+  if (lane == 31) base = atomicAdd(q.count, (unsigned)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  unsigned at = base + (unsigned)(incl - mine);
+  for (int c = 0; c < FLAG_VEC; ++c)
+    if (mask >> c & 1u) q.list[at++] = (unsigned)(t * FLAG_VEC + c);
+}
+template <bool MHD, int MODE>
+__global__ void __launch_bounds__(128, 4) floors_queue_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, unsigned long long *counters,
+                                                              unsigned char *zflags, const LazyGhost lazy, const RedoQueue q) {
+  const Lay L(cfg);
+  const unsigned n = *q.count;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const unsigned t = q.list[e];
+    const int b = (int)(t / (unsigned)L.ncell), o = (int)(t % (unsigned)L.ncell);
+    const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
+    floors_body<MHD, MODE>(pack, cfg, cons, counters, zflags, lazy, L, b, k, j, i, o, zflags[(size_t)b * L.ncell + o]);
+  }
+}
+template <bool MHD, int MODE>
+__global__ void __launch_bounds__(128, 4) fixup_queue_kernel(const pb_pack_t pack, const pb_cfg_t cfg, Real *cons, const Region reg,
+                                                             unsigned char *zflags, const RedoQueue q) {
+  const Lay L(cfg);
+  const unsigned n = *q.count;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const unsigned t = q.list[e];
+    const int b = (int)(t / (unsigned)L.ncell), o = (int)(t % (unsigned)L.ncell);
+    const int i = o % L.ni, r = o / L.ni, j = r % L.nj, k = r / L.nj;
+    if (i < reg.i0 || i > reg.i1 || j < reg.j0 || j > reg.j1 || k < reg.k0 || k > reg.k1) continue;
+    fixup_body<MHD, MODE>(pack, cfg, cons, zflags, L, b, k, j, i, o);
+  }
+}
+
 // (Re)build the zone flags from the current primitives and fail field: needed once before the first
 // flag-driven stage and whenever something outside the sequencer has changed p.* or fail.
 template <bool MHD>
@@ -1344,8 +1407,13 @@ static int c2p_workspace(size_t cells, size_t nthr, C2PWorkspace &out) {
   (void)nthr;
   return PB_OK;
 }
+int presize_block_flags(int nblocks); // flux_split_kernels.cu
 // everything the sequencer allocates lazily, sized for this pack up front (CUDA-graph capture may not allocate)
 int presize_workspaces(const pb_pack_t *pack, const pb_cfg_t *cfg, cudaStream_t stream) {
+  {
+    const int rcb = presize_block_flags(pack->nblocks);
+    if (rcb) return rcb;
+  }
   const Lay L(*cfg);
   const size_t cells = (size_t)pack->nblocks * L.ncell;
   RedoQueue rq;
@@ -1451,8 +1519,26 @@ int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int m
   const Region reg = interior(L);
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
-  if (mode != 0 && L.ncell % FLAG_VEC == 0 && (reinterpret_cast<size_t>(zflags) & 15) == 0) {
-    const unsigned gp = grid_for((long long)pack->nblocks * L.ncell / FLAG_VEC, T);
+  if (mode != 0 && L.ncell % FLAG_VEC == 0 && (reinterpret_cast<size_t>(zflags) & 15) == 0 &&
+      (long long)pack->nblocks * L.ncell < (1ll << 32)) {
+    const long long nvec = (long long)pack->nblocks * L.ncell / FLAG_VEC;
+    if (flag_compaction_enabled()) {
+      RedoQueue q;
+      int rc = redo_queue((size_t)pack->nblocks * L.ncell, q, s);
+      if (rc) return rc;
+      cudaMemsetAsync(q.count, 0, sizeof(unsigned), s);
+      flag_compact_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(zflags, nvec, ZF_FAIL, q);
+      const unsigned gq = (unsigned)(sm_count() * 8);
+#define PB_FIXQ(M, MODE) fixup_queue_kernel<M, MODE><<<gq, T, 0, s>>>(*pack, *cfg, cons, reg, zflags, q)
+      if (cfg->mhd) {
+        if (mode == 1) PB_FIXQ(true, 1); else PB_FIXQ(true, 2);
+      } else {
+        if (mode == 1) PB_FIXQ(false, 1); else PB_FIXQ(false, 2);
+      }
+#undef PB_FIXQ
+      return check_launch("fixup_queue_kernel");
+    }
+    const unsigned gp = grid_for(nvec, T);
 #define PB_FIXP(M, MODE) c2p_fixup_packed_kernel<M, MODE><<<gp, T, 0, s>>>(*pack, *cfg, cons, reg, zflags)
     if (cfg->mhd) {
       if (mode == 1) PB_FIXP(true, 1); else PB_FIXP(true, 2);
@@ -1479,8 +1565,26 @@ int launch_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, unsi
   const int T = zone_threads();
   const unsigned grid = grid_for(reg.n() * pack->nblocks, T);
   const LazyGhost lazy{lazy_u0, lazy_ubase, beta};
-  if (mode != 0 && L.ncell % FLAG_VEC == 0 && (reinterpret_cast<size_t>(zflags) & 15) == 0) {
-    const unsigned gp = grid_for((long long)pack->nblocks * L.ncell / FLAG_VEC, T);
+  if (mode != 0 && L.ncell % FLAG_VEC == 0 && (reinterpret_cast<size_t>(zflags) & 15) == 0 &&
+      (long long)pack->nblocks * L.ncell < (1ll << 32)) {
+    const long long nvec = (long long)pack->nblocks * L.ncell / FLAG_VEC;
+    if (flag_compaction_enabled()) {
+      RedoQueue q;
+      int rc = redo_queue((size_t)pack->nblocks * L.ncell, q, s);
+      if (rc) return rc;
+      cudaMemsetAsync(q.count, 0, sizeof(unsigned), s);
+      flag_compact_kernel<<<grid_for(nvec, 256), 256, 0, s>>>(zflags, nvec, mode == 1 ? ZF_FLOOR : ZF_STALE, q);
+      const unsigned gq = (unsigned)(sm_count() * 8);
+#define PB_FLRQ(M, MODE) floors_queue_kernel<M, MODE><<<gq, T, 0, s>>>(*pack, *cfg, cons, counters, zflags, lazy, q)
+      if (cfg->mhd) {
+        if (mode == 1) PB_FLRQ(true, 1); else PB_FLRQ(true, 2);
+      } else {
+        if (mode == 1) PB_FLRQ(false, 1); else PB_FLRQ(false, 2);
+      }
+#undef PB_FLRQ
+      return check_launch("floors_queue_kernel");
+    }
+    const unsigned gp = grid_for(nvec, T);
 #define PB_FLRP(M, MODE) floors_packed_kernel<M, MODE><<<gp, T, 0, s>>>(*pack, *cfg, cons, counters, zflags, lazy)
     if (cfg->mhd) {
       if (mode == 1) PB_FLRP(true, 1); else PB_FLRP(true, 2);
