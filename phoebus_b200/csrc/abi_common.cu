@@ -90,7 +90,7 @@ static int g_flag_compact = [] {
 bool flag_compaction_enabled() { return g_flag_compact != 0; }
 static int g_riemann_blocks = [] {
   const char *e = getenv("PB_RIEMANN_BLOCKS");
-  return (e && e[0] == '0') ? 0 : 1;
+  return (e && e[0] == '1') ? 1 : 0; // measured slower than the per-warp decision (profiles/r02e_variants.txt): off by default
 }();
 bool riemann_block_split_enabled() { return g_riemann_blocks != 0; }
 bool flux_split_enabled() { return g_flux_split != 0; }

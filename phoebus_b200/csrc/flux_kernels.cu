@@ -68,6 +68,8 @@ struct FluxTile {
   int nT1, nT; // transverse extents: fast one, total pencils per block
   int tiles;   // CTAs per block
   int tiles1;  // TMA staging: tiles along the fast transverse axis (a tile is a box: it never wraps to the next row)
+  int row;     // length of a row of the staged tile in shared memory (NS + 4 along x1, TT across; TMA boxes are padded so that
+  int pad;     // they start on a 16-byte boundary of the slab: `pad` leading cells, measured requirement, profiles/r02_tma_probe.txt)
 };
 
 // ---- asynchronous global -> shared staging (LDGSTS): the copies bypass registers, so a CTA has its
@@ -96,7 +98,8 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
   const int b = blockIdx.x / ft.tiles, tile = blockIdx.x % ft.tiles;
   const int NS = ft.NS, TT = ft.TT;
   const int tid = threadIdx.x, nthr = NS * TT;
-  const int plane_in = (NS + 4) * TT, plane = (NS + 1) * TT;
+  const int RS = ft.row;
+  const int plane_in = (DIR == 1) ? RS * TT : RS * (NS + 4), plane = (NS + 1) * TT;
   Real *s_in = smem, *s_ql = smem + NP * plane_in, *s_geo = s_ql + NP * plane;
   int sI, tI;
   if (DIR == 1) {
@@ -135,8 +138,8 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
     st = L.ni * L.nj;
   }
   // entry e of pencil tI in s_in <-> cell (sI = e - 2); my own cell is entry sI + 2
-  const int in0 = (DIR == 1) ? tI * (NS + 4) + sI : sI * TT + tI;
-  const int in_st = (DIR == 1) ? 1 : TT;
+  const int in0 = ((DIR == 1) ? tI * RS + sI : sI * RS + tI) + ft.pad;
+  const int in_st = (DIR == 1) ? 1 : RS;
   const int slot_w = (DIR == 1) ? tI * (NS + 1) + sI + 1 : (sI + 1) * TT + tI; // my ql goes to face s+1
   const int slot_r = (DIR == 1) ? tI * (NS + 1) + sI : sI * TT + tI;           // face s reads cell s-1's ql
   const int o = L.idx(k, j, i);
@@ -147,9 +150,9 @@ __global__ void __launch_bounds__(288, 2) flux_kernel(const pb_pack_t pack, cons
     if (tid == 0) {
       const int r0 = (tile % ft.tiles1) * TT, r1 = tile / ft.tiles1;
       int c0, c1, c2;
-      if (DIR == 1) c0 = L.is - 3, c1 = L.js - L.dj + r0, c2 = L.ks - L.dk + r1;
-      else if (DIR == 2) c0 = L.is - 1 + r0, c1 = L.js - 3, c2 = L.ks - L.dk + r1;
-      else c0 = L.is - 1 + r0, c1 = L.js - 1 + r1, c2 = L.ks - 3;
+      if (DIR == 1) c0 = L.is - 3 - ft.pad, c1 = L.js - L.dj + r0, c2 = L.ks - L.dk + r1;
+      else if (DIR == 2) c0 = L.is - 1 + r0 - ft.pad, c1 = L.js - 3, c2 = L.ks - L.dk + r1;
+      else c0 = L.is - 1 + r0 - ft.pad, c1 = L.js - 1 + r1, c2 = L.ks - 3;
       mbar_expect_tx(&s_bar, (unsigned)(NP * plane_in * sizeof(Real)));
       tma_load_5d(s_in, &tmap, &s_bar, c0, c1, c2, 0, b);
     }
@@ -320,26 +323,41 @@ static int launch_dir(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStream_t s
   if (ft.TT > ft.nT) ft.TT = ft.nT;
   while (ft.NS * ft.TT > 288 && ft.TT > 1) ft.TT--;
   if (ft.NS * ft.TT > 288) return set_error(PB_EINVAL, "block too large for the flux tile");
-  // TMA staging needs a rectangular tile: TT pencils of ONE row (<= the row length, even along i for the 16-byte rule)
+  // TMA staging needs a rectangular tile: TT pencils of ONE row, and a box that starts on a 16-byte boundary of the slab
+  // (even cell index) with an even number of cells per row
   bool tma = flux_tma_enabled() && L.ni % 2 == 0;
   int TTt = ft.TT > n1 ? n1 : ft.TT;
-  if (DIR == 1) tma = tma && (ft.NS + 4) % 2 == 0;
-  else {
+  int row, pad;
+  if (DIR == 1) {
+    const int start = L.is - 3;
+    pad = ((start % 2) + 2) % 2;
+    row = (ft.NS + 4 + pad + 1) & ~1;
+  } else {
     TTt &= ~1;
     tma = tma && TTt >= 2;
+    pad = (L.is - 1) & 1;
+    row = TTt + 2 * pad;
   }
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof tmap);
   if (tma) {
-    ft.TT = TTt;
-    const cuuint32_t S = (cuuint32_t)(ft.NS + 4), T = (cuuint32_t)ft.TT;
-    const cuuint32_t box[5] = {DIR == 1 ? S : T, DIR == 1 ? T : (DIR == 2 ? S : 1u), DIR == 3 ? S : 1u, (cuuint32_t)NC<MHD>::nprim, 1u};
+    const cuuint32_t S = (cuuint32_t)(ft.NS + 4), R = (cuuint32_t)row;
+    const cuuint32_t box[5] = {R, DIR == 1 ? (cuuint32_t)TTt : (DIR == 2 ? S : 1u), DIR == 3 ? S : 1u, (cuuint32_t)NC<MHD>::nprim, 1u};
     tma = encode_prim_map(pack, cfg, NC<MHD>::nprim, box, &tmap);
+  }
+  if (tma) {
+    ft.TT = TTt;
+    ft.row = row;
+    ft.pad = pad;
+  } else {
+    ft.row = DIR == 1 ? ft.NS + 4 : ft.TT;
+    ft.pad = 0;
   }
   ft.tiles1 = tma ? (n1 + ft.TT - 1) / ft.TT : 0;
   ft.tiles = tma ? ft.tiles1 * n2 : (ft.nT + ft.TT - 1) / ft.TT;
   const int threads = ft.NS * ft.TT;
-  const size_t smem = ((size_t)NC<MHD>::nprim * ((ft.NS + 1) + (ft.NS + 4)) * ft.TT + (size_t)FLUX_NGEO * threads) * sizeof(Real);
+  const size_t plane_in = DIR == 1 ? (size_t)ft.row * ft.TT : (size_t)ft.row * (ft.NS + 4);
+  const size_t smem = ((size_t)NC<MHD>::nprim * ((size_t)(ft.NS + 1) * ft.TT + plane_in) + (size_t)FLUX_NGEO * threads) * sizeof(Real);
   if (tma) {
     auto kern = flux_kernel<DIR, RECON, MHD, true>;
     if (smem > 48 * 1024) {
