@@ -45,6 +45,16 @@ def ncu_kernel_metrics(kernel):
     return None
 
 
+_STDOUT_FD = None
+
+
+def emit(obj):
+    """the one JSON line, on the process's real stdout"""
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, line)
+
+
 def deck_text(name="torus3d"):
     with open(os.path.join(ROOT, "phoebus_b200", "decks", name + ".pin")) as f:
         return f.read()
@@ -326,7 +336,7 @@ def run_ours(args):
         out["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -469,10 +479,16 @@ def run_reference(args):
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "zone-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.time() - t0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
+    # exactly ONE line on stdout: libraries that write there on their own (NCCL prints its version banner at communicator
+    # creation when NCCL_DEBUG is set) are sent to stderr until the JSON line is printed
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -491,10 +507,14 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(_STDOUT_FD, 1)
 
 
 if __name__ == "__main__":

@@ -10,13 +10,14 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
 fi
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29711"
 Q="--gpus $N --steps 8 --warmup 3 --no-cpu-baseline"
-for mode in "weak:" "weak_torch:--halo torch" "strong:--strong" "strong_graphs:--strong --graphs" "weak_graphs:--graphs"; do
+IFS=';' read -ra MODELIST <<< "${MODES:-weak:;weak_torch:--halo torch;strong:--strong;strong_graphs:--strong --graphs;weak_graphs:--graphs}"
+for mode in "${MODELIST[@]}"; do
   name=${mode%%:*}; args=${mode#*:}
   timeout 900 $TR bench.py $Q $args > $OUT/${TAG}_${name}_${N}gpu.json 2> $OUT/${TAG}_${name}_${N}gpu.err
   python - "$OUT/${TAG}_${name}_${N}gpu.json" <<'PY' | tee -a $OUT/${TAG}_summary_${N}gpu.txt
 import json,sys
 try:
-    d=json.load(open(sys.argv[1])); print("%-40s n=%d ms/cycle %.3f zc/s %.4e e2e %s launches %s" % (sys.argv[1].split("/")[-1], d["n_gpus"], d["ms_per_step"], d["value"], d.get("e2e",{}).get("value"), d.get("gpu_launches")))
+    d=json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith("{")][-1]); print("%-40s n=%d ms/cycle %.3f zc/s %.4e e2e %s launches %s" % (sys.argv[1].split("/")[-1], d["n_gpus"], d["ms_per_step"], d["value"], d.get("e2e",{}).get("value"), d.get("gpu_launches")))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
