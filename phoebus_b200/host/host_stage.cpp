@@ -21,17 +21,23 @@
 
 static const char *kFields[] = {"prim", "temp", "c2p_mu", "fail", "csig", "fsig", "base", "1"};
 
+// The state file always describes the WHOLE mesh (blocks in global order, x1 fastest); with world > 1 every rank loads its
+// own MeshBlocks from it and writes them, in its local order, to <path>.rank<r>.
 static void LoadState(Mesh &m, const std::string &path) {
   std::ifstream f(path, std::ios::binary);
   if (!f) throw std::runtime_error("cannot open " + path);
   for (const char *name : kFields) {
-    std::vector<double> buf((size_t)m.FieldWords(name));
-    f.read((char *)buf.data(), (std::streamsize)(buf.size() * 8));
+    const size_t per_block = (size_t)m.FieldWords(name) / (size_t)m.nblocks;
+    std::vector<double> all(per_block * (size_t)m.NumBlocksTotal()), buf((size_t)m.FieldWords(name));
+    f.read((char *)all.data(), (std::streamsize)(all.size() * 8));
     if (!f) throw std::runtime_error("short read of field " + std::string(name));
+    for (int n = 0; n < m.nblocks; ++n)
+      std::memcpy(buf.data() + (size_t)n * per_block, all.data() + (size_t)m.Gid(m.lx[n]) * per_block, per_block * 8);
     m.Upload(name, buf.data());
   }
 }
-static void SaveState(const Mesh &m, const std::string &path, const std::vector<double> &extra) {
+static void SaveState(const Mesh &m, const std::string &path0, const std::vector<double> &extra) {
+  const std::string path = m.world > 1 ? path0 + ".rank" + std::to_string(m.rank) : path0;
   std::ofstream f(path, std::ios::binary);
   for (const char *name : kFields) {
     std::vector<double> buf((size_t)m.FieldWords(name));
@@ -67,10 +73,19 @@ int main(int argc, char *argv[]) {
                   c.ox1_inflow_check);
       std::printf("nblocks %d\nnprim %d\nncons %d\ngeom_words %zu\nfloor_words %zu\n", mesh.nblocks, mesh.nprim, mesh.ncons,
                   mesh.geom_host().size(), mesh.floor_host().size());
+      std::printf("rank %d\nworld %d\nrgrid %d %d %d\nnsend %zu\nnrecv %zu\nnpeers %zu\n", mesh.rank, mesh.world, mesh.rgrid[0], mesh.rgrid[1],
+                  mesh.rgrid[2], mesh.send_plan.size() / 10, mesh.recv_plan.size() / 10, mesh.peers.size());
       std::ofstream f(argv[3], std::ios::binary);
       f.write((const char *)mesh.blocks_host.data(), (std::streamsize)(mesh.blocks_host.size() * sizeof(pb_block_t)));
       f.write((const char *)mesh.geom_host().data(), (std::streamsize)(mesh.geom_host().size() * 8));
       f.write((const char *)mesh.floor_host().data(), (std::streamsize)(mesh.floor_host().size() * 8));
+      // inter-GPU halo plans (world > 1): send rows, receive rows, then per peer {rank, send offset, send count, recv offset, recv count}
+      f.write((const char *)mesh.send_plan.data(), (std::streamsize)(mesh.send_plan.size() * sizeof(int)));
+      f.write((const char *)mesh.recv_plan.data(), (std::streamsize)(mesh.recv_plan.size() * sizeof(int)));
+      for (size_t q = 0; q < mesh.peers.size(); ++q) {
+        const long long row[5] = {mesh.peers[q], mesh.send_off[q], mesh.send_cnt[q], mesh.recv_off[q], mesh.recv_cnt[q]};
+        f.write((const char *)row, sizeof row);
+      }
       return 0;
     }
     const bool fused = std::string(argv[5]) == "fused";

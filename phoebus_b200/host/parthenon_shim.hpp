@@ -159,6 +159,21 @@ class Mesh {
   Packages_t packages;
   pb_cfg_t cfg{};
   int ndim = 1, ng = 0, nblocks = 0;
+  // domain decomposition by MeshBlock (ref: external/parthenon/src/mesh/mesh-amr_loadbalance.cpp:362-389; compact
+  // bricks here): one process per GPU, <phoebus_b200> rank / world (or PB_RANK / PB_WORLD in the environment)
+  int rank = 0, world = 1;
+  int rgrid[3] = {1, 1, 1}, brick[3] = {1, 1, 1};
+  int Owner(const std::array<int, 3> &l) const {
+    return (l[0] / brick[0]) + rgrid[0] * ((l[1] / brick[1]) + rgrid[1] * (l[2] / brick[2]));
+  }
+  long long Gid(const std::array<int, 3> &l) const { return l[0] + (long long)nblk[0] * (l[1] + (long long)nblk[1] * l[2]); }
+  int NumBlocksTotal() const { return nblk[0] * nblk[1] * nblk[2]; }
+  // inter-GPU halo: plans as pb_halo_pack expects them, all peers in one send / one receive buffer
+  std::vector<int> send_plan, recv_plan;                 // rows of 10 ints
+  std::vector<int> peers;
+  std::vector<long long> send_off, send_cnt, recv_off, recv_cnt; // slices of the buffers, in doubles
+  pb_halo_plan_t plan{};
+  void *comm = nullptr;                                  // pb_comm_init handle (world > 1)
   int nx[3] = {1, 1, 1}, nblk[3] = {1, 1, 1}, ncell[3] = {1, 1, 1}; // per block, ghosts included
   long long cells = 0;                                               // ncell[0]*ncell[1]*ncell[2]
   int nprim = 0, ncons = 0;
@@ -192,6 +207,9 @@ class Mesh {
 
  private:
   void BuildBlocks(ParameterInput *pin);
+  void BuildHaloPlans();
+  void InitComm(ParameterInput *pin);
+  std::map<long long, int> local_index_;
   void BuildTables(ParameterInput *pin);
   void Allocate();
   double *Slab(const std::string &name) const;

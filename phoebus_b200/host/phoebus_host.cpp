@@ -1,6 +1,11 @@
 // Host side of the B200 fluid path: deck reader, package Initialize functions, the Mesh (block
 // table, coordinates, tables, device slabs) and the reference-named task functions, each a thin
 // forward to the C ABI of libphoebus_b200.so. See phoebus_host.hpp for the reference citations.
+#include <algorithm>
+#include <chrono>
+#include <fstream>
+#include <thread>
+
 #include "phoebus_host.hpp"
 
 #include <cfloat>
@@ -396,20 +401,58 @@ Mesh::Mesh(ParameterInput *pin, Packages_t pkgs) : packages(std::move(pkgs)) {
   nprim = pb_nprim(&cfg);
   ncons = pb_ncons(&cfg);
 
+  // ---- which blocks are mine: compact bricks, largest factors of the rank count on the dimensions with the most blocks
+  const char *er = std::getenv("PB_RANK"), *ew = std::getenv("PB_WORLD");
+  rank = pin->GetOrAddInteger("phoebus_b200", "rank", er ? std::atoi(er) : 0);
+  world = pin->GetOrAddInteger("phoebus_b200", "world", ew ? std::atoi(ew) : 1);
+  if (world < 1 || rank < 0 || rank >= world) Fail("phoebus_b200/rank must be in [0, world)");
+  {
+    std::vector<int> factors;
+    int w = world;
+    for (int f = 2; w > 1; ++f)
+      while (w % f == 0) {
+        factors.push_back(f);
+        w /= f;
+      }
+    std::sort(factors.rbegin(), factors.rend());
+    for (int f : factors) {
+      int best = -1;
+      for (int d = 0; d < ndim; ++d)
+        if ((nblk[d] / rgrid[d]) % f == 0 && (best < 0 || nblk[d] / rgrid[d] >= nblk[best] / rgrid[best])) best = d;
+      if (best < 0) Fail("cannot decompose the MeshBlocks over " + std::to_string(world) + " ranks");
+      rgrid[best] *= f;
+    }
+    for (int d = 0; d < 3; ++d) brick[d] = nblk[d] / rgrid[d];
+  }
+
   BuildBlocks(pin);
   BuildTables(pin);
-  if (pin->GetOrAddBoolean("phoebus_b200", "allocate", true)) Allocate();
+  if (world > 1) BuildHaloPlans();
+  if (pin->GetOrAddBoolean("phoebus_b200", "allocate", true)) {
+    if (world > 1) {
+      int ndev = 0;
+      CheckCuda(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
+      const char *lr = std::getenv("PB_LOCAL_RANK");
+      CheckCuda(cudaSetDevice((lr ? std::atoi(lr) : rank) % std::max(1, ndev)), "cudaSetDevice");
+    }
+    Allocate();
+    if (world > 1) InitComm(pin);
+  }
 }
 
 void Mesh::BuildBlocks(ParameterInput *) {
-  nblocks = nblk[0] * nblk[1] * nblk[2];
+  nblocks = brick[0] * brick[1] * brick[2];
   lx.resize(nblocks);
   blocks_host.assign(nblocks, pb_block_t{});
+  const int rc[3] = {rank % rgrid[0], (rank / rgrid[0]) % rgrid[1], rank / (rgrid[0] * rgrid[1])};
+  for (int n = 0; n < nblocks; ++n) { // x1 fastest inside the brick
+    lx[n] = {rc[0] * brick[0] + n % brick[0], rc[1] * brick[1] + (n / brick[0]) % brick[1], rc[2] * brick[2] + n / (brick[0] * brick[1])};
+    local_index_[Gid(lx[n])] = n;
+  }
   // the forest is made of trees of pow2^ndim blocks (ref: forest.cpp:70-145)
   int pow2 = 1 << 30;
   for (int d = 0; d < ndim; ++d) pow2 = std::min(pow2, nblk[d] & (~(nblk[d] - 1)));
   for (int n = 0; n < nblocks; ++n) {
-    lx[n] = {n % nblk[0], (n / nblk[0]) % nblk[1], n / (nblk[0] * nblk[1])};
     pb_block_t &b = blocks_host[n];
     for (int d = 0; d < 3; ++d) {
       const double xmin = mesh_xmin_[d], xmax = mesh_xmax_[d];
@@ -449,7 +492,12 @@ void Mesh::BuildBlocks(ParameterInput *) {
             }
             nl[d] = l;
           }
-          b.nbr[code] = none ? PB_NBR_NONE : nl[0] + nblk[0] * (nl[1] + nblk[1] * nl[2]);
+          if (none) {
+            b.nbr[code] = PB_NBR_NONE;
+          } else {
+            const std::array<int, 3> l = {nl[0], nl[1], nl[2]};
+            b.nbr[code] = Owner(l) == rank ? local_index_.at(Gid(l)) : PB_NBR_REMOTE;
+          }
         }
   }
 }
@@ -491,6 +539,135 @@ void Mesh::BuildTables(ParameterInput *) {
     }
     blocks_host[n].floor_slot = ft->second;
   }
+}
+
+// Inter-GPU halo plans (mirror of phoebus_b200/mesh.py: halo_plans / merged_halo_plans): for every peer rank the slabs I
+// send and the ghost slabs I receive, both sides ordered by (gid of the receiving block, offset code seen from the
+// receiver), all peers concatenated into one send and one receive buffer.
+void Mesh::BuildHaloPlans() {
+  struct Seg {
+    long long gid;
+    int code, block, r[3][2];
+  };
+  const int nvar = ncons + (cfg.bc_prim ? nprim + 3 : 0);
+  std::map<int, std::vector<Seg>> send, recv;
+  auto ranges = [&](const int off[3], bool ghost, int r[3][2]) {
+    for (int d = 0; d < 3; ++d) {
+      const int n = d < ndim ? nx[d] : 1, g = d < ndim ? ng : 0, lo = d < ndim ? ng : 0;
+      if (off[d] == 0) r[d][0] = lo, r[d][1] = lo + n - 1;
+      else if (ghost) {
+        if (off[d] < 0) r[d][0] = 0, r[d][1] = g - 1;
+        else r[d][0] = lo + n, r[d][1] = lo + n + g - 1;
+      } else {
+        if (off[d] > 0) r[d][0] = lo + n - g, r[d][1] = lo + n - 1;
+        else r[d][0] = lo, r[d][1] = lo + g - 1;
+      }
+    }
+  };
+  for (int n = 0; n < nblocks; ++n)
+    for (int o3 = (ndim >= 3 ? -1 : 0); o3 <= (ndim >= 3 ? 1 : 0); ++o3)
+      for (int o2 = (ndim >= 2 ? -1 : 0); o2 <= (ndim >= 2 ? 1 : 0); ++o2)
+        for (int o1 = -1; o1 <= 1; ++o1) {
+          if (o1 == 0 && o2 == 0 && o3 == 0) continue;
+          const int off[3] = {o1, o2, o3}, moff[3] = {-o1, -o2, -o3};
+          std::array<int, 3> nl;
+          bool none = false;
+          for (int d = 0; d < 3; ++d) {
+            int l = lx[n][d] + off[d];
+            if (l < 0 || l >= nblk[d]) {
+              if (d < ndim && periodic_[d]) l = (l + nblk[d]) % nblk[d];
+              else none = true;
+            }
+            nl[d] = l;
+          }
+          if (none) continue;
+          const int peer = Owner(nl);
+          if (peer == rank) continue;
+          auto code = [](const int o[3]) { return (o[0] + 1) + 3 * (o[1] + 1) + 9 * (o[2] + 1); };
+          Seg r{Gid(lx[n]), code(off), n, {}}, s{Gid(nl), code(moff), n, {}};
+          ranges(off, true, r.r);
+          ranges(off, false, s.r);
+          recv[peer].push_back(r);
+          send[peer].push_back(s);
+        }
+  std::vector<int> all;
+  for (auto &kv : send) all.push_back(kv.first);
+  for (auto &kv : recv)
+    if (!send.count(kv.first)) all.push_back(kv.first);
+  std::sort(all.begin(), all.end());
+  long long so = 0, ro = 0;
+  for (int peer : all) {
+    long long cnt[2] = {0, 0};
+    for (int side = 0; side < 2; ++side) {
+      std::vector<Seg> &lst = side == 0 ? send[peer] : recv[peer];
+      std::stable_sort(lst.begin(), lst.end(), [](const Seg &a, const Seg &b) { return a.gid != b.gid ? a.gid < b.gid : a.code < b.code; });
+      std::vector<int> &rows = side == 0 ? send_plan : recv_plan;
+      const long long base = side == 0 ? so : ro;
+      for (const Seg &g : lst) {
+        const long long nz = (long long)(g.r[0][1] - g.r[0][0] + 1) * (g.r[1][1] - g.r[1][0] + 1) * (g.r[2][1] - g.r[2][0] + 1);
+        const unsigned long long off = (unsigned long long)(base + cnt[side]);
+        const int row[10] = {g.block, g.r[0][0], g.r[0][1], g.r[1][0], g.r[1][1], g.r[2][0], g.r[2][1], (int)(unsigned)(off & 0xFFFFFFFFull),
+                             (int)(unsigned)(off >> 32), 0};
+        rows.insert(rows.end(), row, row + 10);
+        cnt[side] += nz * nvar;
+      }
+    }
+    peers.push_back(peer);
+    send_off.push_back(so), send_cnt.push_back(cnt[0]);
+    recv_off.push_back(ro), recv_cnt.push_back(cnt[1]);
+    so += cnt[0];
+    ro += cnt[1];
+  }
+}
+
+// NCCL communicator owned by the C library. The 128-byte unique id travels through a rendezvous file
+// (<phoebus_b200> rendezvous or PB_RENDEZVOUS; an MPI build would MPI_Bcast it): rank 0 writes, the others poll.
+void Mesh::InitComm(ParameterInput *pin) {
+  const char *env = std::getenv("PB_RENDEZVOUS");
+  const std::string path = pin->GetOrAddString("phoebus_b200", "rendezvous", env ? env : "");
+  if (path.empty()) Fail("world > 1 needs <phoebus_b200> rendezvous = <file> (or PB_RENDEZVOUS)");
+  char id[128];
+  if (rank == 0) {
+    CheckPb(pb_comm_unique_id(id), "pb_comm_unique_id");
+    const std::string tmp = path + ".tmp";
+    std::ofstream f(tmp, std::ios::binary);
+    f.write(id, 128);
+    f.close();
+    if (std::rename(tmp.c_str(), path.c_str()) != 0) Fail("cannot write the rendezvous file " + path);
+  } else {
+    bool ok = false;
+    for (int tries = 0; tries < 6000 && !ok; ++tries) {
+      std::ifstream f(path, std::ios::binary);
+      if (f && f.read(id, 128) && f.gcount() == 128) ok = true;
+      else std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+    if (!ok) Fail("timed out waiting for the rendezvous file " + path);
+  }
+  CheckPb(pb_comm_init(&comm, rank, world, id), "pb_comm_init");
+  // plans and buffers on the device
+  auto dev = [&](size_t bytes) {
+    void *p = nullptr;
+    CheckCuda(cudaMalloc(&p, bytes ? bytes : 8), "cudaMalloc");
+    owned_.push_back(p);
+    return p;
+  };
+  int *sp = (int *)dev(send_plan.size() * sizeof(int)), *rp = (int *)dev(recv_plan.size() * sizeof(int));
+  if (!send_plan.empty()) CheckCuda(cudaMemcpy(sp, send_plan.data(), send_plan.size() * sizeof(int), cudaMemcpyHostToDevice), "send plan H2D");
+  if (!recv_plan.empty()) CheckCuda(cudaMemcpy(rp, recv_plan.data(), recv_plan.size() * sizeof(int), cudaMemcpyHostToDevice), "recv plan H2D");
+  long long stot = 0, rtot = 0;
+  for (size_t q = 0; q < peers.size(); ++q) stot += send_cnt[q], rtot += recv_cnt[q];
+  plan.send_plan = sp;
+  plan.nsend = (int)(send_plan.size() / 10);
+  plan.recv_plan = rp;
+  plan.nrecv = (int)(recv_plan.size() / 10);
+  plan.send_buf = (double *)dev((size_t)stot * 8);
+  plan.recv_buf = (double *)dev((size_t)rtot * 8);
+  plan.npeers = (int)peers.size();
+  plan.peer = peers.data();
+  plan.send_off = send_off.data();
+  plan.send_cnt = send_cnt.data();
+  plan.recv_off = recv_off.data();
+  plan.recv_cnt = recv_cnt.data();
 }
 
 void Mesh::Allocate() {
@@ -567,6 +744,7 @@ void Mesh::Allocate() {
 }
 
 Mesh::~Mesh() {
+  if (comm) pb_comm_destroy(comm);
   for (void *p : owned_) cudaFree(p);
 }
 
@@ -697,6 +875,8 @@ Real DtImpl(PackView *rc) {
   const double big = DBL_MAX;
   CheckCuda(cudaMemcpyAsync(pm->dt_dev, &big, sizeof big, cudaMemcpyHostToDevice, (cudaStream_t)pm->stream), "dt init");
   CheckPb(pb_estimate_dt(&rc->pack, Cfg(rc), pm->has_face_speeds ? 1 : 0, pm->dt_dev, S(rc)), "pb_estimate_dt");
+  if (pm->comm && rc->nblocks == pm->nblocks) // the mesh-wide estimate: MPI_Allreduce(MIN) in the reference (parthenon driver.cpp:237)
+    CheckPb(pb_comm_allreduce_min(pm->comm, pm->dt_dev, 1, pm->stream), "pb_comm_allreduce_min");
   double dt = 0;
   CheckCuda(cudaMemcpyAsync(&dt, pm->dt_dev, sizeof dt, cudaMemcpyDeviceToHost, (cudaStream_t)pm->stream), "dt D2H");
   pm->Synchronize();
@@ -812,12 +992,20 @@ TaskStatus ApplyBoundaryConditions(std::shared_ptr<T> &) {
 template TaskStatus ApplyBoundaryConditions<MeshBlockData<Real>>(std::shared_ptr<MeshBlockData<Real>> &);
 template TaskStatus ApplyBoundaryConditions<MeshData<Real>>(std::shared_ptr<MeshData<Real>> &);
 
+// ref: boundary_communication.cpp:49-158 (SendBoundBufs), :160-231 (ReceiveBoundBufs), :233-346 (SetBounds). Neighbours on
+// other GPUs: pack + grouped ncclSend / ncclRecv inside pb_halo_exchange_begin, join + unpack in SetBounds.
 TaskStatus SendBoundBufs(std::shared_ptr<MeshData<Real>> &md) {
-  CheckPb(pb_halo_exchange_local(&md->pack, &md->pmesh->cfg, md->cons, md->pmesh->stream), "pb_halo_exchange_local");
+  Mesh *pm = md->pmesh;
+  if (pm->comm) CheckPb(pb_halo_exchange_begin(&md->pack, &pm->cfg, md->cons, &pm->plan, pm->comm, pm->stream), "pb_halo_exchange_begin");
+  CheckPb(pb_halo_exchange_local(&md->pack, &pm->cfg, md->cons, pm->stream), "pb_halo_exchange_local");
   return TaskStatus::complete;
 }
 TaskStatus ReceiveBoundBufs(std::shared_ptr<MeshData<Real>> &) { return TaskStatus::complete; }
-TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &) { return TaskStatus::complete; }
+TaskStatus SetBounds(std::shared_ptr<MeshData<Real>> &md) {
+  Mesh *pm = md->pmesh;
+  if (pm->comm) CheckPb(pb_halo_exchange_end(&md->pack, &pm->cfg, md->cons, &pm->plan, pm->comm, pm->stream), "pb_halo_exchange_end");
+  return TaskStatus::complete;
+}
 
 namespace Update {
 template <class T>
@@ -905,7 +1093,16 @@ TaskStatus PhoebusDriver::RungeKuttaStage(int stage) {
       CheckPb(pb_scan_zone_flags(&base->pack, &pm->cfg, pm->stream), "pb_scan_zone_flags");
       pm->flags_valid = true;
     }
-    CheckPb(pb_rk_stage(&sc0->pack, &pm->cfg, sc0->cons, base->cons, sc1->cons, b, dt, pm->counters, pm->stream), "pb_rk_stage");
+    if (!pm->comm) {
+      CheckPb(pb_rk_stage(&sc0->pack, &pm->cfg, sc0->cons, base->cons, sc1->cons, b, dt, pm->counters, pm->stream), "pb_rk_stage");
+      return TaskStatus::complete;
+    }
+    // N GPUs: the transfer is hidden under the con2prim of the MeshBlocks away from the mesh boundary
+    CheckPb(pb_rk_stage_pre(&sc0->pack, &pm->cfg, sc0->cons, base->cons, sc1->cons, b, dt, pm->counters, pm->stream), "pb_rk_stage_pre");
+    SendBoundBufs(sc1);
+    CheckPb(pb_rk_stage_post_early(&sc1->pack, &pm->cfg, sc1->cons, pm->stream), "pb_rk_stage_post_early");
+    SetBounds(sc1);
+    CheckPb(pb_rk_stage_post2(&sc1->pack, &pm->cfg, sc1->cons, pm->counters, 1, pm->stream), "pb_rk_stage_post2");
     return TaskStatus::complete;
   }
   // ---- the reference's task list, one task at a time (ref: phoebus_driver.cpp:316-365, 556-597, 655-676)

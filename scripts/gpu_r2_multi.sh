@@ -6,7 +6,7 @@ TAG=${TAG:-r02m}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi --query-gpu=index,name --format=csv > $OUT/${TAG}_gpus.txt
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
-  timeout 1500 python -m pytest tests/test_multirank.py -m gpu -q -x -rs 2>&1 | tail -12 | tee $OUT/${TAG}_pytest_multirank_${N}gpu.txt
+  timeout 1500 python -m pytest tests/test_multirank.py tests/test_host_cpp.py -m gpu -q -x -rs -k "nccl or two_gpus" 2>&1 | tail -12 | tee $OUT/${TAG}_pytest_multirank_${N}gpu.txt
 fi
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29711"
 Q="--gpus $N --steps 8 --warmup 3 --no-cpu-baseline"

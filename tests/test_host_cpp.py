@@ -192,3 +192,98 @@ def test_host_driver_long_run_with_its_own_dt_control(mode, tmp_path):
         for k in ("prim", "temp", "c2p_mu", "fail", "csig"):
             assert np.array_equal(out[k][n].reshape(ref[k].shape), ref[k], equal_nan=True), (mode, k)
         assert np.array_equal(out[last["sc1"]][n], ref["cons"], equal_nan=True), (mode, "cons")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# N GPUs: MeshBlock bricks, inter-GPU halo plans and the NCCL exchange of the C library driven by the C++ host layer
+def _brick_deck(tmp_path, mesh_nx=(64, 32, 32), block=16):
+    import bench
+    from phoebus_b200.params import FluidParams, ParameterInput
+    from phoebus_b200.pgen import torus_problem_modifier
+    ov = ["parthenon/mesh/nx%d=%d" % (d + 1, mesh_nx[d]) for d in range(3)]
+    ov += ["parthenon/meshblock/nx%d=%d" % (d + 1, block) for d in range(3)]
+    pin = ParameterInput(bench.deck_text(), ov)
+    torus_problem_modifier(pin)
+    fp = FluidParams(pin)
+    path = os.path.join(str(tmp_path), "brick.pin")
+    with open(path, "w") as f:
+        f.write(_deck_text(pin))
+    return fp, path
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_host_brick_decomposition_and_halo_plans_match_python_mirror(world, tmp_path):
+    """every rank's block table (REMOTE neighbour markers included) and its merged inter-GPU halo plans, C++ vs Python"""
+    from phoebus_b200._lib import PbBlock
+    from phoebus_b200.mesh import MeshPack
+    fp, deck = _brick_deck(tmp_path)
+    for rank in range(world):
+        mesh = MeshPack(fp, rank=rank, world=world, alloc_fields=False)
+        tab = os.path.join(str(tmp_path), "tables_%d.bin" % rank)
+        r = subprocess.run([EXE, "describe", deck, tab, "phoebus_b200/rank=%d" % rank, "phoebus_b200/world=%d" % world],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = {ln.split()[0]: ln.split()[1:] for ln in r.stdout.splitlines() if ln.strip()}
+        assert [int(x) for x in got["rgrid"]] == list(mesh.rgrid) and int(got["nblocks"][0]) == mesh.nblocks
+        raw = open(tab, "rb").read()
+        nb = C.sizeof(PbBlock) * mesh.nblocks
+        assert raw[:nb] == bytes(mesh.blocks_host), "block table of rank %d" % rank
+        sp, stot, rp, rtot, peers = mesh.merged_halo_plans()
+        nd = mesh.geom_host.size + mesh.floor_host.size
+        rest = raw[nb + 8 * nd:]
+        ns, nr = int(got["nsend"][0]), int(got["nrecv"][0])
+        assert (ns, nr, int(got["npeers"][0])) == (len(sp), len(rp), len(peers))
+        plans = np.frombuffer(rest[:40 * (ns + nr)], dtype=np.int32).reshape(-1, 10)
+        assert np.array_equal(plans[:ns], sp) and np.array_equal(plans[ns:], rp), "halo plans of rank %d" % rank
+        tail = np.frombuffer(rest[40 * (ns + nr):], dtype=np.int64).reshape(-1, 5)
+        want = [[p, ss.start, ss.stop - ss.start, rs.start, rs.stop - rs.start] for p, ss, rs in peers]
+        assert tail.tolist() == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fused", "tasks"])
+def test_host_driver_on_two_gpus_matches_one_gpu(mode, tmp_path):
+    """two phoebus_host_stage processes, one per GPU, each owning a brick of MeshBlocks (NCCL halo exchange inside the C
+    library, rendezvous through a file) against the same deck on one GPU: every field of every block, bit for bit"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import bench
+    from phoebus_b200.driver import FluidDriver
+    from phoebus_b200.mesh import MeshPack
+    fp, deck = _brick_deck(tmp_path)
+    mesh = MeshPack(fp, device=torch.device("cuda:0"))
+    drv = FluidDriver(mesh)
+    bench.init_state(mesh, drv)
+    dt = 0.05 * drv.estimate_dt()
+    torch.cuda.synchronize()
+    fields = [getattr(mesh, k) for k in STATE_FIELDS] + [mesh.cons["base"], mesh.cons["1"]]
+    sin = os.path.join(str(tmp_path), "in.bin")
+    with open(sin, "wb") as f:
+        for t in fields:
+            f.write(t.cpu().numpy().tobytes())
+    stages = "1:%r,2:%r,1:%r,2:%r" % (dt, dt, dt, dt)
+    one = os.path.join(str(tmp_path), "one.bin")
+    r = subprocess.run([EXE, "run", deck, sin, one, mode, stages], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    two = os.path.join(str(tmp_path), "two.bin")
+    rdv = os.path.join(str(tmp_path), "nccl_id")
+    procs = [subprocess.Popen([EXE, "run", deck, sin, two, mode, stages],
+                              env=dict(os.environ, PB_RANK=str(rk), PB_WORLD="2", PB_LOCAL_RANK=str(rk), PB_RENDEZVOUS=rdv),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for rk in range(2)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    ref = np.fromfile(one, dtype=np.float64)
+    off = 0
+    parts = [MeshPack(fp, rank=rk, world=2, alloc_fields=False) for rk in range(2)]
+    raws = [np.fromfile(two + ".rank%d" % rk, dtype=np.float64) for rk in range(2)]
+    offs = [0, 0]
+    for k, t in zip(STATE_FIELDS + ("base", "1"), fields):
+        per = t[0].numel()
+        whole = ref[off:off + t.numel()].reshape(mesh.nblocks, per)
+        off += t.numel()
+        for rk, part in enumerate(parts):
+            mine = raws[rk][offs[rk]:offs[rk] + part.nblocks * per].reshape(part.nblocks, per)
+            offs[rk] += part.nblocks * per
+            for n, lx in enumerate(part.lx):
+                assert np.array_equal(mine[n], whole[mesh.local_index[lx]], equal_nan=True), (mode, k, rk, lx)
