@@ -308,6 +308,9 @@ int pb_rk_stage_post(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1,
  * remote ghosts have arrived; _post2(early_done = 1) then runs the BCs, con2prim on everything else, fixup and floors.
  * _post2(early_done = 0) == pb_rk_stage_post. Results are bit-identical either way. */
 int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, void *stream);
+/* 1 if the early / late split of con2prim pays for this pack (at least a third of its MeshBlocks touch no mesh boundary), else 0:
+ * callers then skip pb_rk_stage_post_early and pass early_done = 0 (fewer launches; what a small pack needs) */
+int pb_early_c2p_pays(const pb_pack_t *pack);
 int pb_rk_stage_post2(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, unsigned long long *counters,
                       int early_done, void *stream);
 

@@ -119,6 +119,7 @@ SYMBOLS = {
     "pb_rk_stage_pre": (C.c_int, [_PACK, _CFG, _P, _P, _P, C.c_double, C.c_double, _P, _P]),
     "pb_rk_stage_post": (C.c_int, [_PACK, _CFG, _P, _P, _P]),
     "pb_rk_stage_post_early": (C.c_int, [_PACK, _CFG, _P, _P]),
+    "pb_early_c2p_pays": (C.c_int, [_PACK]),
     "pb_rk_stage_post2": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P]),
 }
 

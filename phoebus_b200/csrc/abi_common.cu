@@ -88,6 +88,11 @@ static int g_flag_compact = [] {
   return (e && e[0] == 'p') ? 0 : 1; // packed (16 zones per thread, serial) | compact (queue, one zone per thread; default)
 }();
 bool flag_compaction_enabled() { return g_flag_compact != 0; }
+static int g_recon_cpt = [] {
+  const char *e = getenv("PB_RECON_CPT");
+  return (e && e[0] == '2') ? 2 : 1;
+}();
+int recon_cells_per_thread() { return g_recon_cpt; }
 static int g_riemann_blocks = [] {
   const char *e = getenv("PB_RIEMANN_BLOCKS");
   return (e && e[0] == '1') ? 1 : 0; // measured slower than the per-warp decision (profiles/r02e_variants.txt): off by default
@@ -232,6 +237,7 @@ extern "C" int pb_set_option(const char *key, int value) {
   if (key && !strcmp(key, "flux_split")) g_flux_split = value != 0;
   else if (key && !strcmp(key, "flux_tma")) g_flux_tma = value != 0;
   else if (key && !strcmp(key, "flag_compact")) g_flag_compact = value != 0;
+  else if (key && !strcmp(key, "recon_cpt") && (value == 1 || value == 2)) g_recon_cpt = value;
   else if (key && !strcmp(key, "riemann_blocks")) g_riemann_blocks = value != 0;
   else if (key && !strcmp(key, "c2p_arith") && value >= 0 && value <= 3) g_c2p_arith = value;
   else return set_error(PB_EINVAL, "pb_set_option: unknown key or value");
@@ -241,6 +247,7 @@ extern "C" int pb_get_option(const char *key) {
   if (key && !strcmp(key, "flux_split")) return g_flux_split;
   if (key && !strcmp(key, "flux_tma")) return g_flux_tma;
   if (key && !strcmp(key, "flag_compact")) return g_flag_compact;
+  if (key && !strcmp(key, "recon_cpt")) return g_recon_cpt;
   if (key && !strcmp(key, "riemann_blocks")) return g_riemann_blocks;
   if (key && !strcmp(key, "c2p_arith")) return g_c2p_arith;
   return set_error(PB_EINVAL, "pb_get_option: unknown key");
@@ -330,6 +337,15 @@ extern "C" int pb_rk_stage_pre(const pb_pack_t *pack, const pb_cfg_t *cfg, doubl
 // boundary must wait: with bc_vars = primitive the boundary fill copies the previous stage's primitives of their
 // interior. pb_rk_stage_post2(early_done = 1) then does the rest: BCs, con2prim on the ghost shells of the inner
 // blocks and on the entire boundary blocks, fixup, floors. Zones are independent, so the bits do not change.
+// Whether starting con2prim under an inter-GPU transfer pays for this pack: the split turns one con2prim task into three
+// (interiors of the inner MeshBlocks, their ghost shells, the boundary blocks); with few inner blocks (strong scaling: 16
+// blocks per GPU) the extra launches cost more than the hidden transfer (measured at 8 GPUs).
+extern "C" int pb_early_c2p_pays(const pb_pack_t *pack) {
+  if (!pack || !pack->inner_blocks || !pack->bc_blocks || pack->n_inner_blocks <= 0) return 0;
+  if (pack->n_inner_blocks + pack->n_bc_blocks != pack->nblocks) return 0;
+  return 3 * pack->n_inner_blocks >= pack->nblocks ? 1 : 0;
+}
+
 extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;

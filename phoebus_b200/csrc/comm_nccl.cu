@@ -213,9 +213,10 @@ extern "C" int pb_stage_graph_create(const pb_pack_t *pack, const pb_cfg_t *cfg,
     rc = pb_rk_stage_pre(pack, cfg, sc0, base, sc1, beta, 0.0, counters, stream);
     if (!rc) rc = pb_halo_exchange_begin(pack, cfg, sc1, plan, comm, stream);
     if (!rc) rc = pb_halo_exchange_local(pack, cfg, sc1, stream);
-    if (!rc) rc = pb_rk_stage_post_early(pack, cfg, sc1, stream);
+    const int early = pb_early_c2p_pays(pack);
+    if (!rc && early) rc = pb_rk_stage_post_early(pack, cfg, sc1, stream);
     if (!rc) rc = pb_halo_exchange_end(pack, cfg, sc1, plan, comm, stream);
-    if (!rc) rc = pb_rk_stage_post2(pack, cfg, sc1, counters, 1, stream);
+    if (!rc) rc = pb_rk_stage_post2(pack, cfg, sc1, counters, early, stream);
   }
   set_stage_dt_pointer(nullptr);
   StageGraph *g = new StageGraph;

@@ -120,6 +120,89 @@ __global__ void __launch_bounds__(PB_RECON_T, PB_RECON_MINB) recon_kernel(const 
   }
 }
 
+// Two cells per thread (option recon_cpt = 2): the pair is taken ALONG the stencil for DIR >= 2 — six loads per primitive
+// instead of ten, rows along i stay coalesced — and along x2 for DIR == 1 (no shared loads there, but two independent
+// reconstructions per thread to hide the FP64 and load latencies). Same arithmetic per cell, same bits.
+#ifndef PB_RECON2_T
+#define PB_RECON2_T 128
+#endif
+#ifndef PB_RECON2_MINB
+#define PB_RECON2_MINB 4
+#endif
+template <int DIR, int RECON, int NP>
+__global__ void __launch_bounds__(PB_RECON2_T, PB_RECON2_MINB) recon2_kernel(const Real *__restrict__ prim, Real *__restrict__ ql,
+                                                                      Real *__restrict__ qr, const pb_cfg_t cfg, const Box reg,
+                                                                      const int nblocks, int *__restrict__ bflag) {
+  constexpr int PD = DIR == 1 ? 2 : DIR; // the paired dimension
+  const Lay L(cfg);
+  Box half = reg; // one thread per PAIR along PD
+  const int npd = (PD == 2 ? reg.j1 - reg.j0 : reg.k1 - reg.k0) + 1;
+  if (PD == 2) half.j1 = half.j0 + (npd + 1) / 2 - 1;
+  else half.k1 = half.k0 + (npd + 1) / 2 - 1;
+  int b, k, j, i;
+  if (!cell_of_thread(half, nblocks, b, k, j, i)) return;
+  if (PD == 2) j = reg.j0 + 2 * (j - reg.j0);
+  else k = reg.k0 + 2 * (k - reg.k0);
+  const bool second = PD == 2 ? (j + 1 <= reg.j1) : (k + 1 <= reg.k1);
+  const int st = DIR == 1 ? 1 : (DIR == 2 ? L.ni : L.ni * L.nj);
+  const int sp = PD == 2 ? L.ni : L.ni * L.nj; // stride between the two cells of the pair
+  const size_t o = (size_t)b * NP * L.ncell + L.idx(k, j, i);
+  const Real *v = prim + o;
+  Real *l = ql + o + st;
+  Real *r = qr + o;
+  ArithFast af;
+  long long anyB = 0;
+#pragma unroll
+  for (int n = 0; n < NP; ++n) {
+    const Real *p = v + (size_t)n * L.ncell;
+    Real qa[5], qb[5];
+    if (DIR == 1) {
+      load_stencil<RECON>(p, st, qa);
+      if (second) load_stencil<RECON>(p + sp, st, qb);
+      else
+        for (int e = 0; e < 5; ++e) qb[e] = qa[e];
+    } else { // sp == st: cell B's stencil is cell A's shifted by one
+      load_stencil<RECON>(p, st, qa);
+      qb[0] = qa[1], qb[1] = qa[2], qb[2] = qa[3], qb[3] = qa[4];
+      qb[4] = (RECON >= 2 && second) ? __ldg(p + 3 * st) : qa[4];
+      if (RECON < 2) { // load_stencil filled the unused slots with the centre value: rebuild B's own
+        qb[2] = second ? __ldg(p + st) : qa[2];
+        qb[1] = RECON >= 1 ? qa[2] : qb[2];
+        qb[3] = (RECON >= 1 && second) ? __ldg(p + 2 * st) : qb[2];
+        qb[0] = qb[4] = qb[2];
+      }
+    }
+    Real a0, c0, a1, c1;
+    recon5z<RECON>(af, qa[0], qa[1], qa[2], qa[3], qa[4], a0, c0);
+    recon5z<RECON>(af, qb[0], qb[1], qb[2], qb[3], qb[4], a1, c1);
+    l[(size_t)n * L.ncell] = a0;
+    r[(size_t)n * L.ncell] = c0;
+    if (second) {
+      l[(size_t)n * L.ncell + sp] = a1;
+      r[(size_t)n * L.ncell + sp] = c1;
+    }
+    if (NP == 10 && n >= PB_ && n < PB_ + 3)
+      anyB |= __double_as_longlong(a0) | __double_as_longlong(c0) | __double_as_longlong(a1) | __double_as_longlong(c1);
+  }
+  if (NP == 10 && bflag && (anyB << 1) != 0) bflag[b] = 1;
+  if (af.failed()) { // operands outside the fast divide's range: redo both cells with the compiler's a/b
+    ArithExact ax;
+    for (int c = 0; c < (second ? 2 : 1); ++c) {
+#pragma unroll 1
+      for (int n = 0; n < NP; ++n) {
+        const Real *p = v + (size_t)n * L.ncell + (size_t)c * sp;
+        Real a, cc;
+        Real q[5];
+        load_stencil<RECON>(p, st, q);
+        recon5z<RECON>(ax, q[0], q[1], q[2], q[3], q[4], a, cc);
+        l[(size_t)n * L.ncell + (size_t)c * sp] = a;
+        r[(size_t)n * L.ncell + (size_t)c * sp] = cc;
+        if (NP == 10 && bflag && n >= PB_ && n < PB_ + 3 && ((__double_as_longlong(a) | __double_as_longlong(cc)) << 1) != 0) bflag[b] = 1;
+      }
+    }
+  }
+}
+
 // One face: load both states and the face geometry, prim_to_flux on each, LLF / HLL, store.
 // Returns the arithmetic policy's failure flag (always false for ArithExact).
 #ifndef PB_RIEMANN_BZ
@@ -276,7 +359,13 @@ static int launch_dir_split(const pb_pack_t &pack, const pb_cfg_t &cfg, cudaStre
     cudaMemsetAsync(bflag, 0, sizeof(int) * pack.nblocks, s);
   }
   prof_begin(PB_TASK_RECON, s);
-  recon_kernel<DIR, RECON, NP><<<(unsigned)((n1 + PB_RECON_T - 1) / PB_RECON_T), PB_RECON_T, 0, s>>>(pack.prim, ql, qr, cfg, rc, pack.nblocks, bflag);
+  if (recon_cells_per_thread() == 2 && L.ndim >= 2) {
+    const int npd = (DIR == 3 ? rc.k1 - rc.k0 : rc.j1 - rc.j0) + 1;
+    const long long nthr = n1 / npd * ((npd + 1) / 2);
+    recon2_kernel<DIR, RECON, NP><<<(unsigned)((nthr + PB_RECON2_T - 1) / PB_RECON2_T), PB_RECON2_T, 0, s>>>(pack.prim, ql, qr, cfg, rc, pack.nblocks, bflag);
+  } else {
+    recon_kernel<DIR, RECON, NP><<<(unsigned)((n1 + PB_RECON_T - 1) / PB_RECON_T), PB_RECON_T, 0, s>>>(pack.prim, ql, qr, cfg, rc, pack.nblocks, bflag);
+  }
   prof_end(PB_TASK_RECON, s);
   int rcode = check_launch("recon_kernel");
   if (rcode) return rcode;

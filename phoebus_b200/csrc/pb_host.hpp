@@ -29,6 +29,7 @@ int need_fields(const char *entry, std::initializer_list<std::pair<const void *,
 int flux_threads_target();
 int zone_threads();
 bool riemann_block_split_enabled(); // option riemann_blocks / PB_RIEMANN_BLOCKS=1|0: unmagnetised MeshBlocks get their own Riemann launch
+int recon_cells_per_thread();   // option recon_cpt / PB_RECON_CPT=1|2: cells per thread in the reconstruction launch
 bool flag_compaction_enabled(); // option flag_compact / PB_FLAG_PASS=compact|packed: flag-driven fixup / floor passes
 bool flux_tma_enabled();   // option flux_tma / PB_FLUX_STAGE=tma|cpasync: how the fused flux kernel stages its stencil tile
 bool flux_split_enabled(); // option flux_split / PB_FLUX_MODE=fused|split (default split when the pack carries ql/qr scratch)

@@ -174,8 +174,10 @@ class FluidDriver:
         else:
             _lib.check(L.pb_rk_stage_pre(pk, cfg, sc0.data_ptr(), base.data_ptr(), sc1.data_ptr(), beta, dt, cnt, s),
                        "pb_rk_stage_pre")
-            # con2prim on the interior of the MeshBlocks away from the mesh boundary runs under the transfer
-            early = lambda: _lib.check(L.pb_rk_stage_post_early(pk, cfg, sc1.data_ptr(), s), "pb_rk_stage_post_early")
+            # con2prim on the interior of the MeshBlocks away from the mesh boundary runs under the transfer, if the pack
+            # has enough of them for the split to pay (pb_early_c2p_pays); force_split always splits (tests)
+            pays = bool(L.pb_early_c2p_pays(pk)) or self.force_split
+            early = (lambda: _lib.check(L.pb_rk_stage_post_early(pk, cfg, sc1.data_ptr(), s), "pb_rk_stage_post_early")) if pays else None
             if self.timers is not None:
                 t = self.torch
                 e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
@@ -185,7 +187,7 @@ class FluidDriver:
                 self.timers.setdefault("halo+early_c2p", []).append((e0, e1))
             else:
                 self.exchange(sc1, early)
-            _lib.check(L.pb_rk_stage_post2(pk, cfg, sc1.data_ptr(), cnt, 1, s), "pb_rk_stage_post2")
+            _lib.check(L.pb_rk_stage_post2(pk, cfg, sc1.data_ptr(), cnt, int(pays), s), "pb_rk_stage_post2")
         self.launches += self.LAUNCHES_PER_STAGE
 
     # kernels launched per stage by pb_rk_stage: flux x ndim, emf + ct, fix, [source,] update
@@ -212,7 +214,8 @@ class FluidDriver:
             n += 2
         if self.dist is not None:
             n += 2  # one pack and one unpack launch for all peers
-            n += 2 * kc  # c2p as three tasks (inner interiors, inner shells, boundary blocks) instead of one
+            if self.L.pb_early_c2p_pays(C.byref(m.pack)):
+                n += 2 * kc  # c2p as three tasks (inner interiors, inner shells, boundary blocks) instead of one
         return n
 
     def enable_profile(self, on=True):

@@ -1100,9 +1100,10 @@ TaskStatus PhoebusDriver::RungeKuttaStage(int stage) {
     // N GPUs: the transfer is hidden under the con2prim of the MeshBlocks away from the mesh boundary
     CheckPb(pb_rk_stage_pre(&sc0->pack, &pm->cfg, sc0->cons, base->cons, sc1->cons, b, dt, pm->counters, pm->stream), "pb_rk_stage_pre");
     SendBoundBufs(sc1);
-    CheckPb(pb_rk_stage_post_early(&sc1->pack, &pm->cfg, sc1->cons, pm->stream), "pb_rk_stage_post_early");
+    const int early = pb_early_c2p_pays(&sc1->pack);
+    if (early) CheckPb(pb_rk_stage_post_early(&sc1->pack, &pm->cfg, sc1->cons, pm->stream), "pb_rk_stage_post_early");
     SetBounds(sc1);
-    CheckPb(pb_rk_stage_post2(&sc1->pack, &pm->cfg, sc1->cons, pm->counters, 1, pm->stream), "pb_rk_stage_post2");
+    CheckPb(pb_rk_stage_post2(&sc1->pack, &pm->cfg, sc1->cons, pm->counters, early, pm->stream), "pb_rk_stage_post2");
     return TaskStatus::complete;
   }
   // ---- the reference's task list, one task at a time (ref: phoebus_driver.cpp:316-365, 556-597, 655-676)

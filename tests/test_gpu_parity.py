@@ -758,3 +758,32 @@ def test_fused_flux_kernel_tma_and_cpasync_match_oracle(name, tma):
     finally:
         L.pb_set_option(b"flux_split", 1)
         L.pb_set_option(b"flux_tma", 1)
+
+
+@pytest.mark.parametrize("name", ["linmodes2d", "blast3d", "torus3d", "torus2d_polar"])
+def test_two_cells_per_thread_reconstruction_matches_oracle(name):
+    """option recon_cpt = 2 (a pair of cells per thread, along the stencil for x2 / x3): all four schemes, fluxes of the oracle"""
+    import torch
+    from phoebus_b200 import _lib
+    L, OL = _lib.lib(), po.lib()
+    try:
+        L.pb_set_option(b"recon_cpt", 2)
+        g, p, mesh, drv, order = _setup(name)
+        om = oracle_mesh(g, p)
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        inv = {n: gid for gid, n in order.items()}
+        ob = {gid: b for gid, b in zip([mb["gid"] for mb in g.manifest("init")["blocks"]], om.blocks)}
+        for recon in range(4):
+            mesh.cfg.recon = recon
+            mesh.flux.zero_()
+            _lib.check(L.pb_calculate_fluxes(C.byref(mesh.pack), C.byref(mesh.cfg), s), "pb_calculate_fluxes")
+            torch.cuda.synchronize()
+            for n in range(mesh.nblocks):
+                b = ob[inv[n]]
+                b.cfg.recon = recon
+                b.flux[:] = 0
+                OL.orc_calculate_fluxes(C.byref(b.cfg), b.geom, b.prim, b.flux, b.fsig)
+                assert np.array_equal(_np(mesh.flux[n]), b.flux), (name, recon, fd.relerr(_np(mesh.flux[n]), b.flux))
+                assert np.array_equal(_np(mesh.fsig[n]), b.fsig), (name, recon)
+    finally:
+        L.pb_set_option(b"recon_cpt", 1)
