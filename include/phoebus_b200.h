@@ -118,7 +118,30 @@ typedef struct pb_pack {
                              * reference's ql / qr fields, ref: src/fluid/fluid.cpp:288-299). When present,
                              * pb_calculate_fluxes runs reconstruction and Riemann solve as two launches per
                              * direction (higher occupancy for the reconstruction); NULL: one fused launch */
+  /* optional ghost plan (pb_ghost_plan_host; all three or none). The stage sequencer then solves con2prim only on
+   * c2p_zones and fills the ghost zones flagged in ghost_mask from the interior zone of their same-pack neighbour AFTER
+   * con2prim: the reference solves those zones twice with identical inputs and tables (ghost_plan_host.cpp). The
+   * task-level entry points (pb_cons_to_prim, pb_halo_exchange_local, ...) ignore the plan. */
+  const unsigned char *ghost_mask; /* device [b][cells]: 1 = deferred ghost zone */
+  const unsigned *c2p_zones;       /* device [c2p_seg[3]]: zone ids b * cells + cell, three segments */
+  long long c2p_seg[4];            /* 0 | interiors of inner_blocks | their other zones | zones of the other blocks */
 } pb_pack_t;
+
+/* Host-side construction of the ghost plan (ghost_plan_host.cpp states the conditions). blocks / geom_host / floor_host
+ * are the HOST copies of what the pack holds on the device; inner_blocks may be NULL (then segments 0 and 1 are empty).
+ * mask_out: nblocks * cells bytes; zones_out: room for nblocks * cells entries; seg_out as pb_pack_t.c2p_seg. The caller
+ * uploads both. Returns PB_OK; a configuration the shortcut does not apply to (bc_vars = conserved, floor type RRhoSie)
+ * yields an all-zero mask and the full zone list. */
+int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks, int nblocks, const double *geom_host,
+                       const double *floor_host, const int *inner_blocks, int n_inner, unsigned char *mask_out,
+                       unsigned *zones_out, long long seg_out[4]);
+/* Same-GPU ghost copy with the plan: phase 0 = every ghost zone (pb_halo_exchange_local); 1 = all but the deferred zones;
+ * 2 = only the deferred zones, every field con2prim reads or writes (conserved, primitives, temperature, c2p_mu, fail,
+ * cell signal speeds, zone flags), to be called after con2prim and before the fixup. */
+int pb_halo_exchange_local_ex(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int phase, void *stream);
+/* 1 when pb_rk_stage / pb_rk_stage_post_early / pb_rk_stage_post2 use the pack's ghost plan (plan present, bc_vars =
+ * primitive, option ghost_plan on): the phase a caller that issues the same-GPU ghost copy of a stage itself has to pass. */
+int pb_ghost_plan_active(const pb_pack_t *pack, const pb_cfg_t *cfg);
 
 const char *pb_version(void);
 const char *pb_last_error(void);
@@ -350,6 +373,9 @@ int pb_profile_read(double ms[PB_NTASK], int calls[PB_NTASK]);
  *   "c2p_arith"  2|3|0|1 (PB_C2P_ARITH=queue|split|exact|inline) con2prim: one launch with warp-level parking of slowly
  *                converging zones + redo queue for the zones ArithFast rejects (default); root find and unwrap as separate
  *                launches (same parking); the compiler's divide / sqrt; ArithFast with an inline exact re-solve.
+ *   "recon_cpt"  1|2  (PB_RECON_CPT=1|2) cells per thread in the reconstruction launch of the split flux path (2 was
+ *                measured slower, profiles/r02g_variants.txt)
+ *   "ghost_plan" 1|0  (PB_GHOST_PLAN=1|0) the stage sequencer uses the pack's ghost plan (pb_ghost_plan_host) when present
  *                All settings produce identical bits. */
 int pb_set_option(const char *key, int value);
 int pb_get_option(const char *key);

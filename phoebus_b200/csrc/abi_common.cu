@@ -98,6 +98,10 @@ static int g_riemann_blocks = [] {
   return (e && e[0] == '1') ? 1 : 0; // measured slower than the per-warp decision (profiles/r02e_variants.txt): off by default
 }();
 bool riemann_block_split_enabled() { return g_riemann_blocks != 0; }
+static int g_ghost_plan = [] {
+  const char *e = getenv("PB_GHOST_PLAN");
+  return (e && e[0] == '0') ? 0 : 1; // use pack->ghost_mask / c2p_zones when the pack carries them
+}();
 bool flux_split_enabled() { return g_flux_split != 0; }
 bool flux_tma_enabled() { return g_flux_tma != 0; }
 int c2p_arith_mode() { return g_c2p_arith; }
@@ -239,6 +243,7 @@ extern "C" int pb_set_option(const char *key, int value) {
   else if (key && !strcmp(key, "flag_compact")) g_flag_compact = value != 0;
   else if (key && !strcmp(key, "recon_cpt") && (value == 1 || value == 2)) g_recon_cpt = value;
   else if (key && !strcmp(key, "riemann_blocks")) g_riemann_blocks = value != 0;
+  else if (key && !strcmp(key, "ghost_plan")) g_ghost_plan = value != 0;
   else if (key && !strcmp(key, "c2p_arith") && value >= 0 && value <= 3) g_c2p_arith = value;
   else return set_error(PB_EINVAL, "pb_set_option: unknown key or value");
   return PB_OK;
@@ -249,6 +254,7 @@ extern "C" int pb_get_option(const char *key) {
   if (key && !strcmp(key, "flag_compact")) return g_flag_compact;
   if (key && !strcmp(key, "recon_cpt")) return g_recon_cpt;
   if (key && !strcmp(key, "riemann_blocks")) return g_riemann_blocks;
+  if (key && !strcmp(key, "ghost_plan")) return g_ghost_plan;
   if (key && !strcmp(key, "c2p_arith")) return g_c2p_arith;
   return set_error(PB_EINVAL, "pb_get_option: unknown key");
 }
@@ -282,6 +288,8 @@ int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const i
                unsigned char *zflags, cudaStream_t s);
 int launch_c2p_list(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, int which,
                     unsigned char *zflags, cudaStream_t s);
+int launch_c2p_zones(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, long long from, long long to,
+                     unsigned char *zflags, cudaStream_t s);
 int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int mode, unsigned char *zflags, cudaStream_t s);
 int launch_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, unsigned long long *counters, int mode,
                   unsigned char *zflags, const double *lazy_u0, const double *lazy_ubase, double beta, cudaStream_t s);
@@ -346,6 +354,13 @@ extern "C" int pb_early_c2p_pays(const pb_pack_t *pack) {
   return 3 * pack->n_inner_blocks >= pack->nblocks ? 1 : 0;
 }
 
+// Whether the stage sequencer uses the pack's ghost plan (ghost_plan_host.cpp): callers that issue the same-GPU ghost copy
+// themselves (inter-GPU exchange) pass phase = pb_ghost_plan_active(...) to pb_halo_exchange_local_ex.
+extern "C" int pb_ghost_plan_active(const pb_pack_t *pack, const pb_cfg_t *cfg) {
+  if (!pack || !cfg || !g_ghost_plan || !cfg->bc_prim) return 0;
+  return (pack->ghost_mask && pack->c2p_zones && pack->c2p_seg[3] > 0) ? 1 : 0;
+}
+
 extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
@@ -354,6 +369,7 @@ extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg
     return set_error(PB_EINVAL, "pb_rk_stage_post_early: inner_blocks and bc_blocks must partition the pack");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope p(PB_TASK_C2P, s);
+  if (pb_ghost_plan_active(pack, cfg)) return launch_c2p_zones(pack, cfg, sc1, pack->c2p_seg[0], pack->c2p_seg[1], pack->zflags, s);
   return launch_c2p_list(pack, cfg, sc1, pack->inner_blocks, pack->n_inner_blocks, 0, pack->zflags, s);
 }
 
@@ -373,7 +389,17 @@ extern "C" int pb_rk_stage_post2(const pb_pack_t *pack, const pb_cfg_t *cfg, dou
   }
   const Lay L(*cfg);
   const int ib[2] = {0, L.ni - 1}, jb[2] = {0, L.nj - 1}, kb[2] = {0, L.nk - 1};
-  {
+  const bool plan = pb_ghost_plan_active(pack, cfg) != 0;
+  if (plan) {
+    // con2prim where it has to be solved, then the deferred ghost zones take the neighbour's result (before the fixup,
+    // which reads ghost primitives and fail flags as con2prim left them)
+    {
+      ProfScope p(PB_TASK_C2P, s);
+      if ((rc = launch_c2p_zones(pack, cfg, sc1, split ? pack->c2p_seg[1] : pack->c2p_seg[0], pack->c2p_seg[3], pack->zflags, s))) return rc;
+    }
+    ProfScope p(PB_TASK_HALO, s);
+    if ((rc = pb_halo_exchange_local_ex(pack, cfg, sc1, 2, stream))) return rc;
+  } else {
     ProfScope p(PB_TASK_C2P, s);
     if (split) {
       if ((rc = launch_c2p_list(pack, cfg, sc1, pack->inner_blocks, pack->n_inner_blocks, 1, pack->zflags, s))) return rc;
@@ -407,7 +433,7 @@ extern "C" int pb_rk_stage(const pb_pack_t *pack, const pb_cfg_t *cfg, double *s
   // region 8: ghost exchange
   {
     ProfScope p(PB_TASK_HALO, (cudaStream_t)stream);
-    if ((rc = pb_halo_exchange_local(pack, cfg, sc1, stream))) return rc;
+    if ((rc = pb_halo_exchange_local_ex(pack, cfg, sc1, pb_ghost_plan_active(pack, cfg), stream))) return rc;
   }
   return pb_rk_stage_post(pack, cfg, sc1, counters, stream);
 }

@@ -212,7 +212,7 @@ extern "C" int pb_stage_graph_create(const pb_pack_t *pack, const pb_cfg_t *cfg,
   } else {
     rc = pb_rk_stage_pre(pack, cfg, sc0, base, sc1, beta, 0.0, counters, stream);
     if (!rc) rc = pb_halo_exchange_begin(pack, cfg, sc1, plan, comm, stream);
-    if (!rc) rc = pb_halo_exchange_local(pack, cfg, sc1, stream);
+    if (!rc) rc = pb_halo_exchange_local_ex(pack, cfg, sc1, pb_ghost_plan_active(pack, cfg), stream);
     const int early = pb_early_c2p_pays(pack);
     if (!rc && early) rc = pb_rk_stage_post_early(pack, cfg, sc1, stream);
     if (!rc) rc = pb_halo_exchange_end(pack, cfg, sc1, plan, comm, stream);

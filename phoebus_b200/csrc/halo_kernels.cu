@@ -38,7 +38,14 @@ static HaloFields halo_fields(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *
   return f;
 }
 
-__global__ void halo_local_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const HaloFields hf) {
+// One thread per ghost zone. All components of a field group are loaded before any is stored: source and
+// destination live in the same arrays, so the compiler cannot hoist loads over stores by itself, and a zone's
+// 8 (conserved) or 8 + 13 (with bc_vars = primitive) words would otherwise be that many serial DRAM round trips.
+// PHASE (ghost plan, ghost_plan_host.cpp): 0 every ghost zone; 1 skip the zones flagged in pack.ghost_mask; 2 only
+// those, after con2prim, with the cell signal speeds and the zone flags on top of the exchanged fields.
+template <bool MHD, bool PRIM, int PHASE>
+__global__ void __launch_bounds__(256) halo_local_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const HaloFields hf) {
+  constexpr int NCn = NC<MHD>::ncons, NP = NC<MHD>::nprim;
   const Lay L(cfg);
   const Shell sh(L);
   const int N = L.ncell;
@@ -48,6 +55,10 @@ __global__ void halo_local_kernel(const pb_pack_t pack, const pb_cfg_t cfg, cons
   int i, j, k;
   sh.cell(L, (int)(t % sh.n), k, j, i);
   const int o = L.idx(k, j, i);
+  if (PHASE != 0) {
+    const bool deferred = pack.ghost_mask[(size_t)b * N + o] != 0;
+    if (deferred != (PHASE == 2)) return;
+  }
   const int o1 = i < L.is ? -1 : (i > L.ie ? 1 : 0);
   const int o2 = j < L.js ? -1 : (j > L.je ? 1 : 0);
   const int o3 = k < L.ks ? -1 : (k > L.ke ? 1 : 0);
@@ -56,22 +67,33 @@ __global__ void halo_local_kernel(const pb_pack_t pack, const pb_cfg_t cfg, cons
   if (nb < 0) return;
   const int si = i - o1 * cfg.nx[0], sj = j - o2 * cfg.nx[1], sk = k - o3 * cfg.nx[2];
   const int so = L.idx(sk, sj, si);
-  for (int f = 0; f < hf.nfield; ++f) {
-    const int nc = hf.ncomp[f];
-    const Real *src = hf.ptr[f] + (size_t)nb * nc * N + so;
-    Real *dst = hf.ptr[f] + (size_t)b * nc * N + o;
-    int n = 0;
-#ifndef PB_HALO_ILP
-#define PB_HALO_ILP 4
-#endif
-    for (; n + PB_HALO_ILP <= nc; n += PB_HALO_ILP) { // independent loads in flight per thread (the copy is latency bound otherwise)
-      Real v[PB_HALO_ILP];
+  {
+    const Real *src = hf.ptr[0] + (size_t)nb * NCn * N + so;
+    Real *dst = hf.ptr[0] + (size_t)b * NCn * N + o;
+    Real v[NCn];
 #pragma unroll
-      for (int u = 0; u < PB_HALO_ILP; ++u) v[u] = src[(size_t)(n + u) * N];
+    for (int n = 0; n < NCn; ++n) v[n] = src[(size_t)n * N];
 #pragma unroll
-      for (int u = 0; u < PB_HALO_ILP; ++u) dst[(size_t)(n + u) * N] = v[u];
-    }
-    for (; n < nc; ++n) dst[(size_t)n * N] = src[(size_t)n * N];
+    for (int n = 0; n < NCn; ++n) dst[(size_t)n * N] = v[n];
+  }
+  if (PRIM) {
+    const Real *src = hf.ptr[1] + (size_t)nb * NP * N + so;
+    Real *dst = hf.ptr[1] + (size_t)b * NP * N + o;
+    Real v[NP], w[3];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) v[n] = src[(size_t)n * N];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) w[f] = hf.ptr[2 + f][(size_t)nb * N + so];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) dst[(size_t)n * N] = v[n];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) hf.ptr[2 + f][(size_t)b * N + o] = w[f];
+  }
+  if (PHASE == 2) {
+    Real c[3];
+    for (int d = 0; d < L.ndim; ++d) c[d] = pack.csig[((size_t)nb * L.ndim + d) * N + so];
+    for (int d = 0; d < L.ndim; ++d) pack.csig[((size_t)b * L.ndim + d) * N + o] = c[d];
+    if (pack.zflags) pack.zflags[(size_t)b * N + o] = pack.zflags[(size_t)nb * N + so];
   }
 }
 
@@ -125,16 +147,40 @@ extern "C" int pb_halo_nvar(const pb_cfg_t *cfg) {
   return NCn + (cfg->bc_prim ? NP + 3 : 0);
 }
 
-extern "C" int pb_halo_exchange_local(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {
+extern "C" int pb_halo_exchange_local_ex(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int phase, void *stream) {
   int rc = check_args(pack, cfg);
   if (rc) return rc;
+  if (phase < 0 || phase > 2) return set_error(PB_EINVAL, "pb_halo_exchange_local_ex: phase must be 0, 1 or 2");
+  if (phase != 0 && !pack->ghost_mask) return set_error(PB_EINVAL, "pb_halo_exchange_local_ex: phase 1 / 2 need pack->ghost_mask");
+  if (phase == 2 && !cfg->bc_prim) return PB_OK; // no zone is ever deferred without bc_vars = primitive
+  if (phase == 2) PB_NEED("pb_halo_exchange_local_ex", PB_F(pack, csig));
   const Lay L(*cfg);
   const Shell sh(L);
   const long long n = (long long)sh.n * pack->nblocks;
   if (n <= 0) return PB_OK;
   const int T = 256;
-  halo_local_kernel<<<(unsigned)((n + T - 1) / T), T, 0, (cudaStream_t)stream>>>(*pack, *cfg, halo_fields(*pack, *cfg, cons));
+  const unsigned G = (unsigned)((n + T - 1) / T);
+  const HaloFields hf = halo_fields(*pack, *cfg, cons);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PB_HALO(M, P)                                                              \
+  do {                                                                             \
+    if (phase == 0) halo_local_kernel<M, P, 0><<<G, T, 0, st>>>(*pack, *cfg, hf);  \
+    else if (phase == 1) halo_local_kernel<M, P, 1><<<G, T, 0, st>>>(*pack, *cfg, hf); \
+    else halo_local_kernel<M, P, 2><<<G, T, 0, st>>>(*pack, *cfg, hf);             \
+  } while (0)
+  if (cfg->mhd) {
+    if (cfg->bc_prim) PB_HALO(true, true);
+    else PB_HALO(true, false);
+  } else {
+    if (cfg->bc_prim) PB_HALO(false, true);
+    else PB_HALO(false, false);
+  }
+#undef PB_HALO
   return check_launch("halo_local_kernel");
+}
+
+extern "C" int pb_halo_exchange_local(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {
+  return pb_halo_exchange_local_ex(pack, cfg, cons, 0, stream);
 }
 
 extern "C" int pb_halo_pack(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, const int *plan, int nseg,

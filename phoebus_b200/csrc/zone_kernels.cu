@@ -388,9 +388,23 @@ struct C2PWork {
   const int *blocks; // block list or NULL (= all blocks of the pack)
   int nlist;         // blocks covered
   int shell;         // 1: ghost shell instead of the box
+  const unsigned *zones; // ghost plan: explicit zone ids (block * ncell + cell), nzones of them; overrides the rest
+  long long nzones;
 };
+PB_DEV bool c2p_zone_of_list(const C2PWork &w, const Lay &L, long long t, int &b, int &k, int &j, int &i) {
+  if (t >= w.nzones) return false;
+  const unsigned z = __ldg(w.zones + t);
+  b = (int)(z / (unsigned)L.ncell);
+  int rem = (int)(z - (unsigned)b * (unsigned)L.ncell);
+  i = rem % L.ni;
+  rem /= L.ni;
+  j = rem % L.nj;
+  k = rem / L.nj;
+  return true;
+}
 PB_DEV bool c2p_zone_of_thread(const C2PWork &w, const Lay &L, int &b, int &k, int &j, int &i) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w.zones) return c2p_zone_of_list(w, L, t, b, k, j, i);
   if (w.shell) {
     const Shell sh(L);
     if (t >= (long long)sh.n * w.nlist) return false;
@@ -500,6 +514,7 @@ struct SolveGeom {
 };
 
 PB_DEV bool c2p_zone_of_index(const C2PWork &w, const Lay &L, long long t, int &b, int &k, int &j, int &i) {
+  if (w.zones) return c2p_zone_of_list(w, L, t, b, k, j, i);
   if (w.shell) {
     const Shell sh(L);
     const int q = (int)(t / sh.n);
@@ -1499,8 +1514,16 @@ int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const i
                unsigned char *zflags, cudaStream_t s) {
   const Region reg{ib[0], ib[1], jb[0], jb[1], kb[0], kb[1]};
   if (reg.n() <= 0) return PB_OK;
-  const C2PWork work{reg, nullptr, pack->nblocks, 0};
+  const C2PWork work{reg, nullptr, pack->nblocks, 0, nullptr, 0};
   return launch_c2p_work(pack, cfg, cons, work, reg.n() * pack->nblocks, zflags, s);
+}
+// c2p on the zones [from, to) of the pack's ghost plan (pack->c2p_zones)
+int launch_c2p_zones(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, long long from, long long to,
+                     unsigned char *zflags, cudaStream_t s) {
+  if (to <= from) return PB_OK;
+  const Lay L(*cfg);
+  const C2PWork work{entire(L), nullptr, pack->nblocks, 0, pack->c2p_zones + from, to - from};
+  return launch_c2p_work(pack, cfg, cons, work, to - from, zflags, s);
 }
 // c2p on a list of blocks: which = 0 interior zones, 1 ghost shell, 2 entire block
 int launch_c2p_list(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, int which,
@@ -1509,7 +1532,7 @@ int launch_c2p_list(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, co
   const Lay L(*cfg);
   const Shell sh(L);
   const Region reg = which == 0 ? interior(L) : entire(L);
-  const C2PWork work{reg, blocks, nlist, which == 1 ? 1 : 0};
+  const C2PWork work{reg, blocks, nlist, which == 1 ? 1 : 0, nullptr, 0};
   const long long nthr = (which == 1 ? (long long)sh.n : reg.n()) * nlist;
   return launch_c2p_work(pack, cfg, cons, work, nthr, zflags, s);
 }

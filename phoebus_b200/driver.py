@@ -91,21 +91,23 @@ class FluidDriver:
             self.comm = None
 
     # ------------------------------------------------------------------ tasks
-    def exchange(self, cons, under_transfer=None):
+    def exchange(self, cons, under_transfer=None, in_stage=False):
         """region 8: SendBoundBufs / ReceiveBoundBufs / SetBounds. `under_transfer`, if given, is called after the
         same-GPU ghost copy has been launched and before the remote ghosts are waited for (work to hide the
-        NVLink transfer under)."""
+        NVLink transfer under). in_stage: the call is followed by pb_rk_stage_post2, which fills the ghost zones the
+        pack's ghost plan defers (include/phoebus_b200.h), so the same-GPU copy may leave them out."""
         m, L = self.m, self.L
         pk, cfg = self._pk()
         s = self._stream()
+        phase = int(L.pb_ghost_plan_active(pk, cfg)) if in_stage else 0
         if self.dist is None:
-            _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
+            _lib.check(L.pb_halo_exchange_local_ex(pk, cfg, cons.data_ptr(), phase, s), "pb_halo_exchange_local_ex")
             if under_transfer is not None:
                 under_transfer()
             return
         if self.comm is not None:
             _lib.check(L.pb_halo_exchange_begin(pk, cfg, cons.data_ptr(), C.byref(self.plan), self.comm, s), "pb_halo_exchange_begin")
-            _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
+            _lib.check(L.pb_halo_exchange_local_ex(pk, cfg, cons.data_ptr(), phase, s), "pb_halo_exchange_local_ex")
             if under_transfer is not None:
                 under_transfer()
             _lib.check(L.pb_halo_exchange_end(pk, cfg, cons.data_ptr(), C.byref(self.plan), self.comm, s), "pb_halo_exchange_end")
@@ -120,7 +122,7 @@ class FluidDriver:
                 ops.append(dist.P2POp(dist.irecv, h["rbuf"], h["peer"]))
         reqs = dist.batch_isend_irecv(ops) if ops else []
         # same-GPU neighbours, then interior work, while the NVLink transfers are in flight
-        _lib.check(L.pb_halo_exchange_local(pk, cfg, cons.data_ptr(), s), "pb_halo_exchange_local")
+        _lib.check(L.pb_halo_exchange_local_ex(pk, cfg, cons.data_ptr(), phase, s), "pb_halo_exchange_local_ex")
         if under_transfer is not None:
             under_transfer()
         for r in reqs:
@@ -182,11 +184,11 @@ class FluidDriver:
                 t = self.torch
                 e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
                 e0.record()
-                self.exchange(sc1, early)
+                self.exchange(sc1, early, in_stage=True)
                 e1.record()
                 self.timers.setdefault("halo+early_c2p", []).append((e0, e1))
             else:
-                self.exchange(sc1, early)
+                self.exchange(sc1, early, in_stage=True)
             _lib.check(L.pb_rk_stage_post2(pk, cfg, sc1.data_ptr(), cnt, int(pays), s), "pb_rk_stage_post2")
         self.launches += self.LAUNCHES_PER_STAGE
 
@@ -212,10 +214,14 @@ class FluidDriver:
             n += 2
         if m.p.enable_floors:
             n += 2
+        plan = bool(self.L.pb_ghost_plan_active(*self._pk()))
+        if plan:
+            n += 1  # the deferred ghost zones are copied after con2prim
         if self.dist is not None:
             n += 2  # one pack and one unpack launch for all peers
             if self.L.pb_early_c2p_pays(C.byref(m.pack)):
-                n += 2 * kc  # c2p as three tasks (inner interiors, inner shells, boundary blocks) instead of one
+                # c2p as three tasks (inner interiors, inner shells, boundary blocks) instead of one; two with the ghost plan
+                n += (1 if plan else 2) * kc
         return n
 
     def enable_profile(self, on=True):

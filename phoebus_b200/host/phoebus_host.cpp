@@ -735,6 +735,27 @@ void Mesh::Allocate() {
   pack_.n_inner_blocks = (int)inner.size();
   pack_.gsrc = field_["gsrc"];
   pack_.recon_lr = (double *)dev((size_t)2 * nblocks * nprim * cells * 8); // ql / qr of one direction
+  // ghost plan: ghost zones whose con2prim result is copied from the same-GPU neighbour (include/phoebus_b200.h)
+  pack_.ghost_mask = nullptr;
+  pack_.c2p_zones = nullptr;
+  for (int n = 0; n < 4; ++n) pack_.c2p_seg[n] = 0;
+  if (cfg.bc_prim) {
+    std::vector<unsigned char> mask((size_t)nblocks * cells);
+    std::vector<unsigned> zones((size_t)nblocks * cells);
+    long long seg[4];
+    CheckPb(pb_ghost_plan_host(&cfg, blocks_host.data(), nblocks, geom_host_.data(), floor_host_.data(),
+                               inner.empty() ? nullptr : inner.data(), (int)inner.size(), mask.data(), zones.data(), seg),
+            "pb_ghost_plan_host");
+    if (seg[3] < (long long)nblocks * cells) {
+      unsigned char *mask_dev = (unsigned char *)dev(mask.size());
+      CheckCuda(cudaMemcpy(mask_dev, mask.data(), mask.size(), cudaMemcpyHostToDevice), "ghost mask H2D");
+      unsigned *zones_dev = (unsigned *)dev(sizeof(unsigned) * (size_t)seg[3]);
+      CheckCuda(cudaMemcpy(zones_dev, zones.data(), sizeof(unsigned) * (size_t)seg[3], cudaMemcpyHostToDevice), "c2p zone list H2D");
+      pack_.ghost_mask = mask_dev;
+      pack_.c2p_zones = zones_dev;
+      for (int n = 0; n < 4; ++n) pack_.c2p_seg[n] = seg[n];
+    }
+  }
   AddContainer("base");
   AddContainer("1");
   AddContainer("dUdt");
@@ -800,6 +821,8 @@ std::shared_ptr<MeshBlockData<Real>> Mesh::GetBlockData(int b, const std::string
   p.n_bc_blocks = 0;
   p.inner_blocks = nullptr;
   p.n_inner_blocks = 0;
+  p.ghost_mask = nullptr; // the plan describes the whole pack
+  p.c2p_zones = nullptr;
   rc->pack = p;
   rc->cons = cons_[stage] + o * (stage == "geometric source terms" ? 4 : ncons);
   return rc;
@@ -1099,7 +1122,9 @@ TaskStatus PhoebusDriver::RungeKuttaStage(int stage) {
     }
     // N GPUs: the transfer is hidden under the con2prim of the MeshBlocks away from the mesh boundary
     CheckPb(pb_rk_stage_pre(&sc0->pack, &pm->cfg, sc0->cons, base->cons, sc1->cons, b, dt, pm->counters, pm->stream), "pb_rk_stage_pre");
-    SendBoundBufs(sc1);
+    CheckPb(pb_halo_exchange_begin(&sc1->pack, &pm->cfg, sc1->cons, &pm->plan, pm->comm, pm->stream), "pb_halo_exchange_begin");
+    CheckPb(pb_halo_exchange_local_ex(&sc1->pack, &pm->cfg, sc1->cons, pb_ghost_plan_active(&sc1->pack, &pm->cfg), pm->stream),
+            "pb_halo_exchange_local_ex");
     const int early = pb_early_c2p_pays(&sc1->pack);
     if (early) CheckPb(pb_rk_stage_post_early(&sc1->pack, &pm->cfg, sc1->cons, pm->stream), "pb_rk_stage_post_early");
     SetBounds(sc1);

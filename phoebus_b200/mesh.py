@@ -54,13 +54,14 @@ def rank_grid(world, nblk, ndim):
 
 class MeshPack:
     def __init__(self, params, device=None, rank=0, world=1, mesh_xmin=None, mesh_xmax=None, geom_par=None,
-                 alloc_fields=True, use_zflags=True, use_gsrc=True, use_recon_lr=True):
+                 alloc_fields=True, use_zflags=True, use_gsrc=True, use_recon_lr=True, use_ghost_plan=True):
         import torch
         self.torch = torch
         self.p = params
         self.rank, self.world = rank, world
         self.device = device
         self.use_zflags, self.use_gsrc, self.use_recon_lr = use_zflags, use_gsrc, use_recon_lr
+        self.use_ghost_plan = use_ghost_plan
         p = params
         self.ndim, self.ng = p.ndim, p.ng
         self.nx = tuple(p.block_nx)
@@ -289,8 +290,44 @@ class MeshPack:
         pk.n_bc_blocks = self.n_bc_blocks
         pk.inner_blocks = self.inner_blocks.data_ptr()
         pk.n_inner_blocks = self.n_inner_blocks
+        self._ghost_plan(pk, inner)
         self.pack = pk
         self.flags_valid = False
+
+    def ghost_plan_host(self, inner=None):
+        """(mask [nblocks*ncell] u8, zones u32, seg[4]) of pb_ghost_plan_host for this pack — host arrays only"""
+        L = _lib.lib()
+        if inner is None:
+            inner = [n for n in range(self.nblocks) if not any(self.blocks_host[n].bc[f] != 0 for f in range(2 * self.ndim))]
+        mask = np.zeros(self.nblocks * self.ncell, dtype=np.uint8)
+        zones = np.zeros(self.nblocks * self.ncell, dtype=np.uint32)
+        seg = (C.c_longlong * 4)()
+        inn = np.ascontiguousarray(inner, dtype=np.int32)
+        cfg = self.p.make_cfg(self.gshape)
+        _lib.check(L.pb_ghost_plan_host(C.byref(cfg), C.addressof(self.blocks_host), self.nblocks, self.geom_host.ctypes.data,
+                                        self.floor_host.ctypes.data, inn.ctypes.data if len(inner) else None, len(inner),
+                                        mask.ctypes.data, zones.ctypes.data, seg), "pb_ghost_plan_host")
+        return mask, zones[:seg[3]].copy(), tuple(seg)
+
+    def _ghost_plan(self, pk, inner):
+        """which ghost zones take their con2prim result from the same-GPU neighbour instead of solving again
+        (pb_ghost_plan_host, csrc/ghost_plan_host.cpp); use_ghost_plan=False leaves the pack without a plan"""
+        t = self.torch
+        self.ghost_mask = self.c2p_zones = None
+        self.c2p_seg, self.n_deferred = (0, 0, 0, 0), 0
+        if not self.use_ghost_plan or not self.p.bc_prim:
+            return
+        mask, zones, seg = self.ghost_plan_host(inner)
+        self.c2p_seg = seg
+        self.n_deferred = int(mask.sum())
+        if self.n_deferred == 0:
+            return
+        self.ghost_mask = t.from_numpy(mask).to(self.device)
+        self.c2p_zones = t.from_numpy(zones).to(self.device)
+        pk.ghost_mask = self.ghost_mask.data_ptr()
+        pk.c2p_zones = self.c2p_zones.data_ptr()
+        for n in range(4):
+            pk.c2p_seg[n] = seg[n]
 
     def zones(self):
         """interior zones owned by this pack"""

@@ -1,0 +1,107 @@
+"""The ghost plan (phoebus_b200/csrc/ghost_plan_host.cpp): ghost zones whose con2prim result the stage sequencer copies
+from the same-GPU neighbour instead of solving again. CPU tests of the host-side plan builder, including the claim the
+shortcut rests on, checked against the UNMODIFIED reference's own per-stage dumps: in every deferred ghost zone the
+reference holds exactly what it holds in the neighbour's interior zone."""
+import numpy as np
+import pytest
+
+from oracle import from_dump as fd
+from tests.helpers import CASES, block_lx, getter, load_case, product_mesh, stage_tags
+
+PRIM_BC = ["torus2d", "torus3d", "torus2d_fail", "torus2d_polar", "reflect2d_prim"]
+
+
+def _plan(name):
+    g, p = load_case(name)
+    mesh, fp = product_mesh(g, alloc_fields=False)
+    mask, zones, seg = mesh.ghost_plan_host()
+    return g, mesh, fp, mask.reshape((mesh.nblocks,) + mesh.shape), zones, seg
+
+
+def _offsets(mesh):
+    """per zone of a block: neighbour-slot code and source cell index"""
+    ng, nd = mesh.ng, mesh.ndim
+    nk, nj, ni = mesh.shape
+    k, j, i = np.meshgrid(np.arange(nk), np.arange(nj), np.arange(ni), indexing="ij")
+    def off(c, n, active):
+        if not active:
+            return np.zeros_like(c)
+        return np.where(c < ng, -1, np.where(c >= ng + n, 1, 0))
+    o1, o2, o3 = off(i, mesh.nx[0], True), off(j, mesh.nx[1], nd >= 2), off(k, mesh.nx[2], nd >= 3)
+    code = (o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)
+    src = ((k - o3 * mesh.nx[2]) * nj + (j - o2 * mesh.nx[1])) * ni + (i - o1 * mesh.nx[0])
+    return (o1, o2, o3), code, src
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_plan_is_a_partition_and_respects_the_conditions(name):
+    g, mesh, fp, mask, zones, seg = _plan(name)
+    ncell = mesh.ncell
+    tot = mesh.nblocks * ncell
+    # zone list + deferred zones = every zone exactly once
+    assert seg[0] == 0 and seg[3] == len(zones) and seg[1] <= seg[2] <= seg[3]
+    seen = np.zeros(tot, dtype=np.int32)
+    np.add.at(seen, zones.astype(np.int64), 1)
+    assert np.array_equal(seen + mask.reshape(-1), np.ones(tot, dtype=np.int32))
+    if not fp.bc_prim:
+        assert mask.sum() == 0
+        return
+    (o1, o2, o3), code, src = _offsets(mesh)
+    ghost = (o1 != 0) | (o2 != 0) | (o3 != 0)
+    inner = [n for n in range(mesh.nblocks) if not any(mesh.blocks_host[n].bc[f] != 0 for f in range(2 * mesh.ndim))]
+    zb = zones.astype(np.int64) // ncell
+    zc = zones.astype(np.int64) % ncell
+    # segments: interiors of the inner blocks | their other zones | the other blocks
+    assert set(zb[:seg[1]]) <= set(inner) and not ghost.reshape(-1)[zc[:seg[1]]].any()
+    assert set(zb[seg[1]:seg[2]]) <= set(inner) and ghost.reshape(-1)[zc[seg[1]:seg[2]]].all()
+    assert not (set(zb[seg[2]:]) & set(inner))
+    assert seg[1] == len(inner) * mesh.nx[0] * mesh.nx[1] * mesh.nx[2] if mesh.ndim == 3 else True
+    for n in range(mesh.nblocks):
+        blk = mesh.blocks_host[n]
+        m = mask[n].astype(bool)
+        assert not (m & ~ghost).any()  # interior zones always solve
+        for d, o in enumerate((o1, o2, o3)):
+            if d >= mesh.ndim:
+                continue
+            # no deferred zone in a face that is not towards another MeshBlock (physical, periodic)
+            if blk.bc[2 * d] != 0:
+                assert not (m & (o == -1)).any()
+            if blk.bc[2 * d + 1] != 0:
+                assert not (m & (o == 1)).any()
+        nb = np.array([blk.nbr[c] for c in range(27)])
+        assert (nb[code[m]] >= 0).all()  # the neighbour lives in this pack
+
+
+@pytest.mark.parametrize("name", PRIM_BC)
+def test_reference_dumps_hold_the_neighbours_result_in_every_deferred_zone(name):
+    g, mesh, fp, mask, zones, seg = _plan(name)
+    if mesh.nblocks == 1 and mask.sum() == 0:
+        pytest.skip("single MeshBlock without a same-pack neighbour")
+    assert mask.sum() > 0, "fixture has neighbouring MeshBlocks but no deferred zone"
+    _, code, src = _offsets(mesh)
+    checked = 0
+    for tag in stage_tags(g):
+        man = g.manifest(tag)
+        get = getter(g, tag)
+        state = {}
+        for mb in man["blocks"]:
+            n = mesh.local_index[block_lx(mesh, man, mb, mesh.ndim, mesh.ng, mesh.nx)]
+            ref = fd.ref_state(get, mb["gid"], mesh.shape, man["sc1"])
+            state[n] = {k: np.asarray(v).reshape((-1, mesh.ncell)) for k, v in ref.items()}
+        for n in range(mesh.nblocks):
+            m = mask[n].reshape(-1).astype(bool)
+            if not m.any():
+                continue
+            nb = np.array([mesh.blocks_host[n].nbr[c] for c in range(27)])[code.reshape(-1)[m]]
+            so = src.reshape(-1)[m]
+            mine = np.nonzero(m)[0]
+            for q in np.unique(nb):
+                sel = nb == q
+                # zones the neighbour's fixup rewrote afterwards (interior only) are excluded
+                good = state[int(q)]["fail"][0, so[sel]] == 1.0
+                for k in ("prim", "temp", "c2p_mu", "fail", "csig", "cons"):
+                    a = state[n][k][:, mine[sel][good]]
+                    b = state[int(q)][k][:, so[sel][good]]
+                    assert np.array_equal(a.view(np.int64), b.view(np.int64)), (name, tag, n, int(q), k)
+                checked += int(good.sum())
+    assert checked > 0

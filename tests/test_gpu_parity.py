@@ -48,7 +48,9 @@ def _setup(name, **kw):
 
 # the sequencer with and without its accelerators (zone flags, separate source launch) must give
 # the same bits: "exhaustive" runs every task over every zone exactly like the reference
-MODES = {"flagged": dict(use_zflags=True, use_gsrc=True), "exhaustive": dict(use_zflags=False, use_gsrc=False)}
+# "noplan": without the ghost plan (every ghost zone runs its own con2prim, as the reference does)
+MODES = {"flagged": dict(use_zflags=True, use_gsrc=True), "exhaustive": dict(use_zflags=False, use_gsrc=False, use_ghost_plan=False),
+         "noplan": dict(use_zflags=True, use_gsrc=True, use_ghost_plan=False), "plan_unflagged": dict(use_zflags=False, use_gsrc=True)}
 
 
 @pytest.mark.parametrize("mode", list(MODES))
@@ -787,3 +789,47 @@ def test_two_cells_per_thread_reconstruction_matches_oracle(name):
                 assert np.array_equal(_np(mesh.fsig[n]), b.fsig), (name, recon)
     finally:
         L.pb_set_option(b"recon_cpt", 1)
+
+
+def _torus_run(block, mesh_nx, cycles, use_ghost_plan, force_split=False, graphs=False):
+    """FM torus on a small 3-D FMKS mesh through the product's own start-up sequence, `cycles` RK2 cycles"""
+    import torch
+    from phoebus_b200.driver import FluidDriver
+    from phoebus_b200.mesh import MeshPack
+    from phoebus_b200.params import FluidParams, ParameterInput
+    from phoebus_b200.pgen import init_torus, torus_problem_modifier
+    ov = ["parthenon/mesh/nx%d=%d" % (d + 1, mesh_nx[d]) for d in range(3)]
+    ov += ["parthenon/meshblock/nx%d=%d" % (d + 1, block) for d in range(3)]
+    ov += ["parthenon/time/dt_init_fact=1e-2"]
+    pin = ParameterInput(open(os.path.join(ROOT_DIR, "phoebus_b200", "decks", "torus3d.pin")).read(), ov)
+    torus_problem_modifier(pin)
+    fp = FluidParams(pin)
+    mesh = MeshPack(fp, device=_dev(), use_ghost_plan=use_ghost_plan)
+    drv = FluidDriver(mesh, use_graphs=graphs)
+    drv.force_split = force_split
+    init_torus(mesh, drv)
+    drv.ensure_flags()
+    mesh.counters.zero_()
+    dt = 1e-2 * drv.estimate_dt()
+    for _ in range(cycles):
+        drv.step(dt)
+    torch.cuda.synchronize()
+    out = {k: _np(getattr(mesh, k)) for k in FIELDS}
+    out["cons"] = _np(mesh.cons["base"])
+    out["counters"] = _np(mesh.counters)
+    return out, mesh
+
+
+@pytest.mark.parametrize("force_split", [False, True])
+def test_ghost_plan_on_a_mesh_with_inner_blocks_changes_no_bit(force_split):
+    """64 MeshBlocks of 16^3 (8 of them away from every mesh boundary, so all three segments of the plan's zone list are
+    populated): two cycles with the ghost plan equal two cycles without it in every field of every zone, ghosts
+    included, and in the floor / failure counters; also with con2prim split around the (here empty) transfer"""
+    ref, mref = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=False)
+    out, mesh = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=True, force_split=force_split)
+    assert mref.ghost_mask is None and mesh.ghost_mask is not None
+    seg = mesh.c2p_seg
+    assert 0 < seg[1] < seg[2] < seg[3] < mesh.nblocks * mesh.ncell
+    assert mesh.n_deferred > 0.2 * mesh.nblocks * mesh.ncell
+    for k in ref:
+        assert np.array_equal(out[k], ref[k], equal_nan=True), k
