@@ -54,7 +54,7 @@ class PbPack(C.Structure):
                 ("csig", C.c_void_p), ("fsig", C.c_void_p), ("flux", C.c_void_p), ("emf", C.c_void_p),
                 ("zflags", C.c_void_p), ("bc_blocks", C.c_void_p), ("n_bc_blocks", C.c_int), ("gsrc", C.c_void_p),
                 ("inner_blocks", C.c_void_p), ("n_inner_blocks", C.c_int), ("recon_lr", C.c_void_p),
-                ("ghost_mask", C.c_void_p), ("c2p_zones", C.c_void_p), ("c2p_seg", C.c_longlong * 6),
+                ("ghost_mask", C.c_void_p), ("c2p_zones", C.c_void_p), ("c2p_seg", C.c_longlong * 4),
                 ("halo_pairs", C.c_void_p), ("halo_seg", C.c_longlong * 3)]
 
 

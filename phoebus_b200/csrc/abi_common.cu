@@ -98,10 +98,6 @@ static int g_riemann_blocks = [] {
   return (e && e[0] == '1') ? 1 : 0; // measured slower than the per-warp decision (profiles/r02e_variants.txt): off by default
 }();
 bool riemann_block_split_enabled() { return g_riemann_blocks != 0; }
-static int g_halo_overlap = [] {
-  const char *e = getenv("PB_HALO_OVERLAP");
-  return (e && e[0] == '0') ? 0 : 1; // deferred ghost copy on a second stream, under the con2prim of the block cores
-}();
 static int g_ghost_plan = [] {
   const char *e = getenv("PB_GHOST_PLAN");
   return (e && e[0] == '0') ? 0 : 1; // use pack->ghost_mask / c2p_zones when the pack carries them
@@ -248,7 +244,6 @@ extern "C" int pb_set_option(const char *key, int value) {
   else if (key && !strcmp(key, "recon_cpt") && (value == 1 || value == 2)) g_recon_cpt = value;
   else if (key && !strcmp(key, "riemann_blocks")) g_riemann_blocks = value != 0;
   else if (key && !strcmp(key, "ghost_plan")) g_ghost_plan = value != 0;
-  else if (key && !strcmp(key, "halo_overlap")) g_halo_overlap = value != 0;
   else if (key && !strcmp(key, "c2p_arith") && value >= 0 && value <= 3) g_c2p_arith = value;
   else return set_error(PB_EINVAL, "pb_set_option: unknown key or value");
   return PB_OK;
@@ -260,7 +255,6 @@ extern "C" int pb_get_option(const char *key) {
   if (key && !strcmp(key, "recon_cpt")) return g_recon_cpt;
   if (key && !strcmp(key, "riemann_blocks")) return g_riemann_blocks;
   if (key && !strcmp(key, "ghost_plan")) return g_ghost_plan;
-  if (key && !strcmp(key, "halo_overlap")) return g_halo_overlap;
   if (key && !strcmp(key, "c2p_arith")) return g_c2p_arith;
   return set_error(PB_EINVAL, "pb_get_option: unknown key");
 }
@@ -360,36 +354,11 @@ extern "C" int pb_early_c2p_pays(const pb_pack_t *pack) {
   return 3 * pack->n_inner_blocks >= pack->nblocks ? 1 : 0;
 }
 
-// Library-owned second stream (highest priority, one per device) for the memory-bound ghost copy that runs beside the
-// FP64-bound con2prim of the block cores: forked from and joined back into the caller's stream by events, so the caller
-// still sees one stream; inside a CUDA-graph capture the fork / join become graph edges.
-namespace pb {
-struct AuxStream {
-  cudaStream_t s = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
-};
-static AuxStream *aux_stream() {
-  static AuxStream per_dev[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  AuxStream &a = per_dev[dev];
-  if (!a.s) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&a.s, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess)
-      return nullptr;
-  }
-  return &a;
-}
-} // namespace pb
-
 // Whether the stage sequencer uses the pack's ghost plan (ghost_plan_host.cpp): callers that issue the same-GPU ghost copy
 // themselves (inter-GPU exchange) pass phase = pb_ghost_plan_active(...) to pb_halo_exchange_local_ex.
 extern "C" int pb_ghost_plan_active(const pb_pack_t *pack, const pb_cfg_t *cfg) {
   if (!pack || !cfg || !g_ghost_plan || !cfg->bc_prim) return 0;
-  return (pack->ghost_mask && pack->c2p_zones && pack->c2p_seg[5] > 0) ? 1 : 0;
+  return (pack->ghost_mask && pack->c2p_zones && pack->c2p_seg[3] > 0) ? 1 : 0;
 }
 
 extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, void *stream) {
@@ -400,10 +369,7 @@ extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg
     return set_error(PB_EINVAL, "pb_rk_stage_post_early: inner_blocks and bc_blocks must partition the pack");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope p(PB_TASK_C2P, s);
-  if (pb_ghost_plan_active(pack, cfg)) { // rind and core of the inner blocks (segments 0 and 4)
-    if ((rc = launch_c2p_zones(pack, cfg, sc1, pack->c2p_seg[0], pack->c2p_seg[1], pack->zflags, s))) return rc;
-    return launch_c2p_zones(pack, cfg, sc1, pack->c2p_seg[4], pack->c2p_seg[5], pack->zflags, s);
-  }
+  if (pb_ghost_plan_active(pack, cfg)) return launch_c2p_zones(pack, cfg, sc1, pack->c2p_seg[0], pack->c2p_seg[1], pack->zflags, s);
   return launch_c2p_list(pack, cfg, sc1, pack->inner_blocks, pack->n_inner_blocks, 0, pack->zflags, s);
 }
 
@@ -427,33 +393,12 @@ extern "C" int pb_rk_stage_post2(const pb_pack_t *pack, const pb_cfg_t *cfg, dou
   if (plan) {
     // con2prim where it has to be solved, then the deferred ghost zones take the neighbour's result (before the fixup,
     // which reads ghost primitives and fail flags as con2prim left them)
-    // Zone-list segments (ghost_plan_host.cpp): 0-2 hold every zone a deferred copy reads (the rinds) and every ghost zone
-    // that is solved; 3-4 the block cores, which nothing but con2prim touches — the copy runs beside their con2prim.
-    const long long *sg = pack->c2p_seg;
     {
       ProfScope p(PB_TASK_C2P, s);
-      if ((rc = launch_c2p_zones(pack, cfg, sc1, split ? sg[1] : sg[0], sg[3], pack->zflags, s))) return rc;
+      if ((rc = launch_c2p_zones(pack, cfg, sc1, split ? pack->c2p_seg[1] : pack->c2p_seg[0], pack->c2p_seg[3], pack->zflags, s))) return rc;
     }
-    AuxStream *aux = g_halo_overlap ? aux_stream() : nullptr;
-    if (aux) {
-      cudaEventRecord(aux->fork, s);
-      cudaStreamWaitEvent(aux->s, aux->fork, 0);
-      {
-        ProfScope p(PB_TASK_HALO, aux->s);
-        if ((rc = pb_halo_exchange_local_ex(pack, cfg, sc1, 2, aux->s))) return rc;
-      }
-      cudaEventRecord(aux->join, aux->s);
-    }
-    {
-      ProfScope p(PB_TASK_C2P, s);
-      if ((rc = launch_c2p_zones(pack, cfg, sc1, sg[3], split ? sg[4] : sg[5], pack->zflags, s))) return rc;
-    }
-    if (aux) {
-      cudaStreamWaitEvent(s, aux->join, 0);
-    } else {
-      ProfScope p(PB_TASK_HALO, s);
-      if ((rc = pb_halo_exchange_local_ex(pack, cfg, sc1, 2, stream))) return rc;
-    }
+    ProfScope p(PB_TASK_HALO, s);
+    if ((rc = pb_halo_exchange_local_ex(pack, cfg, sc1, 2, stream))) return rc;
   } else {
     ProfScope p(PB_TASK_C2P, s);
     if (split) {

@@ -49,7 +49,7 @@ inline bool same_bits(double a, double b) { return std::memcmp(&a, &b, sizeof(do
 
 extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks, int nblocks, const double *geom_host,
                                   const double *floor_host, const int *inner_blocks, int n_inner,
-                                  unsigned char *mask_out, unsigned *zones_out, long long seg_out[6],
+                                  unsigned char *mask_out, unsigned *zones_out, long long seg_out[4],
                                   unsigned *pairs_out, long long pair_seg_out[3]) {
   if (!cfg || !blocks || nblocks <= 0 || !geom_host || !floor_host || !mask_out || !zones_out || !seg_out) return PB_EINVAL;
   const HostLay L(*cfg);
@@ -103,12 +103,7 @@ extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks,
           if (ok) mask_out[(size_t)b * L.ncell + L.idx(k, j, i)] = 1;
         }
   }
-  // zone list in five segments. "rind" = interior zones within ng of a block face (every zone a ghost copy or a physical
-  // ghost fill reads), "core" = the other interior zones (nothing outside con2prim touches them during a stage's post phase):
-  //   0 rind of the inner blocks | 1 their ghost zones that are solved | 2 rind + solved ghost zones of the other blocks |
-  //   3 core of the other blocks | 4 core of the inner blocks
-  // The sequencer solves 0-2, then copies the deferred ghost zones WHILE 3-4 are being solved (abi_common.cu); with an
-  // inter-GPU exchange 0 and 4 run under the transfer.
+  // zone list in three segments: interiors of the inner blocks | their remaining ghost zones | the other blocks
   std::vector<char> inner(nblocks, 0);
   for (int n = 0; n < n_inner && inner_blocks; ++n)
     if (inner_blocks[n] >= 0 && inner_blocks[n] < nblocks) inner[inner_blocks[n]] = 1;
@@ -117,29 +112,17 @@ extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks,
   auto interior = [&](int k, int j, int i) {
     return i >= L.lo[0] && i <= L.hi[0] && j >= L.lo[1] && j <= L.hi[1] && k >= L.lo[2] && k <= L.hi[2];
   };
-  auto core = [&](int k, int j, int i) {
-    const int c[3] = {i, j, k};
-    for (int d = 0; d < L.ndim; ++d)
-      if (c[d] < L.lo[d] + L.ng || c[d] > L.hi[d] - L.ng) return false;
-    return true;
-  };
-  for (int pass = 0; pass < 5; ++pass) {
-    const bool want_inner = pass == 0 || pass == 1 || pass == 4;
+  for (int pass = 0; pass < 3; ++pass) {
     for (int b = 0; b < nblocks; ++b) {
-      if (want_inner != (inner[b] != 0)) continue;
+      if ((pass < 2) != (inner[b] != 0)) continue;
       const unsigned base = (unsigned)((size_t)b * L.ncell);
       for (int k = 0; k < L.nk; ++k)
         for (int j = 0; j < L.nj; ++j)
           for (int i = 0; i < L.ni; ++i) {
             const int o = L.idx(k, j, i);
             if (mask_out[(size_t)base + o]) continue;
-            const bool in = interior(k, j, i), co = in && core(k, j, i);
-            bool take;
-            if (pass == 0) take = in && !co;
-            else if (pass == 1) take = !in;
-            else if (pass == 2) take = !co;
-            else take = co;
-            if (take) zones_out[n++] = base + (unsigned)o;
+            if (pass < 2 && (pass == 0) != interior(k, j, i)) continue;
+            zones_out[n++] = base + (unsigned)o;
           }
     }
     seg_out[pass + 1] = n;

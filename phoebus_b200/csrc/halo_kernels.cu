@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) halo_local_kernel(const pb_pack_t pack, c
 // The same copy driven by the ghost plan's (destination, source) list: no index decoding, no idle lanes — the two phases
 // of a planned stage each visit only their own zones.
 template <bool MHD, bool PRIM, int PHASE>
-__global__ void __launch_bounds__(128) halo_list_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const HaloFields hf,
+__global__ void __launch_bounds__(256) halo_list_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const HaloFields hf,
                                                         const uint2 *__restrict__ pairs, const long long n) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -220,14 +220,13 @@ extern "C" int pb_halo_exchange_local_ex(const pb_pack_t *pack, const pb_cfg_t *
     const long long n = pack->halo_seg[phase] - pack->halo_seg[phase - 1];
     if (n <= 0) return PB_OK;
     const uint2 *pairs = reinterpret_cast<const uint2 *>(pack->halo_pairs) + pack->halo_seg[phase - 1];
-    // 128-thread CTAs: phase 2 shares the SMs with con2prim (abi_common.cu) and has to fit into the registers one of its CTAs frees
-    const unsigned G = (unsigned)((n + 127) / 128);
+    const unsigned G = (unsigned)((n + 255) / 256);
     const HaloFields hf = halo_fields(*pack, *cfg, cons);
     cudaStream_t st = (cudaStream_t)stream;
 #define PB_HALO_L(M, P)                                                                          \
   do {                                                                                           \
-    if (phase == 1) halo_list_kernel<M, P, 1><<<G, 128, 0, st>>>(*pack, *cfg, hf, pairs, n);     \
-    else halo_list_kernel<M, P, 2><<<G, 128, 0, st>>>(*pack, *cfg, hf, pairs, n);                \
+    if (phase == 1) halo_list_kernel<M, P, 1><<<G, 256, 0, st>>>(*pack, *cfg, hf, pairs, n);     \
+    else halo_list_kernel<M, P, 2><<<G, 256, 0, st>>>(*pack, *cfg, hf, pairs, n);                \
   } while (0)
     if (cfg->mhd) {
       if (cfg->bc_prim) PB_HALO_L(true, true);

@@ -215,15 +215,13 @@ class FluidDriver:
         if m.p.enable_floors:
             n += 2
         plan = bool(self.L.pb_ghost_plan_active(*self._pk()))
-        early = self.dist is not None and bool(self.L.pb_early_c2p_pays(C.byref(m.pack)))
         if plan:
-            # the deferred ghost zones are copied after con2prim; con2prim runs as two tasks (rinds + solved ghosts, cores),
-            # four when the inner blocks start under an inter-GPU transfer
-            n += 1 + (3 if early else 1) * kc
-        elif early:
-            n += 2 * kc  # c2p as three tasks (inner interiors, inner shells, boundary blocks) instead of one
+            n += 1  # the deferred ghost zones are copied after con2prim
         if self.dist is not None:
             n += 2  # one pack and one unpack launch for all peers
+            if self.L.pb_early_c2p_pays(C.byref(m.pack)):
+                # c2p as three tasks (inner interiors, inner shells, boundary blocks) instead of one; two with the ghost plan
+                n += (1 if plan else 2) * kc
         return n
 
     def enable_profile(self, on=True):

@@ -739,25 +739,25 @@ void Mesh::Allocate() {
   pack_.ghost_mask = nullptr;
   pack_.c2p_zones = nullptr;
   pack_.halo_pairs = nullptr;
-  for (int n = 0; n < 6; ++n) pack_.c2p_seg[n] = 0;
+  for (int n = 0; n < 4; ++n) pack_.c2p_seg[n] = 0;
   for (int n = 0; n < 3; ++n) pack_.halo_seg[n] = 0;
   if (cfg.bc_prim) {
     std::vector<unsigned char> mask((size_t)nblocks * cells);
     std::vector<unsigned> zones((size_t)nblocks * cells);
-    long long seg[6], pseg[3];
+    long long seg[4], pseg[3];
     std::vector<unsigned> pairs((size_t)2 * nblocks * cells);
     CheckPb(pb_ghost_plan_host(&cfg, blocks_host.data(), nblocks, geom_host_.data(), floor_host_.data(),
                                inner.empty() ? nullptr : inner.data(), (int)inner.size(), mask.data(), zones.data(), seg,
                                pairs.data(), pseg),
             "pb_ghost_plan_host");
-    if (seg[5] < (long long)nblocks * cells) {
+    if (seg[3] < (long long)nblocks * cells) {
       unsigned char *mask_dev = (unsigned char *)dev(mask.size());
       CheckCuda(cudaMemcpy(mask_dev, mask.data(), mask.size(), cudaMemcpyHostToDevice), "ghost mask H2D");
-      unsigned *zones_dev = (unsigned *)dev(sizeof(unsigned) * (size_t)seg[5]);
-      CheckCuda(cudaMemcpy(zones_dev, zones.data(), sizeof(unsigned) * (size_t)seg[5], cudaMemcpyHostToDevice), "c2p zone list H2D");
+      unsigned *zones_dev = (unsigned *)dev(sizeof(unsigned) * (size_t)seg[3]);
+      CheckCuda(cudaMemcpy(zones_dev, zones.data(), sizeof(unsigned) * (size_t)seg[3], cudaMemcpyHostToDevice), "c2p zone list H2D");
       pack_.ghost_mask = mask_dev;
       pack_.c2p_zones = zones_dev;
-      for (int n = 0; n < 6; ++n) pack_.c2p_seg[n] = seg[n];
+      for (int n = 0; n < 4; ++n) pack_.c2p_seg[n] = seg[n];
       unsigned *pairs_dev = (unsigned *)dev(sizeof(unsigned) * 2 * (size_t)std::max<long long>(1, pseg[2]));
       CheckCuda(cudaMemcpy(pairs_dev, pairs.data(), sizeof(unsigned) * 2 * (size_t)pseg[2], cudaMemcpyHostToDevice), "halo pair list H2D");
       pack_.halo_pairs = pairs_dev;

@@ -295,14 +295,14 @@ class MeshPack:
         self.flags_valid = False
 
     def ghost_plan_host(self, inner=None):
-        """(mask [nblocks*ncell] u8, zones u32, seg[6], pairs u32 [n][2], pair_seg[3]) of pb_ghost_plan_host for this
+        """(mask [nblocks*ncell] u8, zones u32, seg[4], pairs u32 [n][2], pair_seg[3]) of pb_ghost_plan_host for this
         pack — host arrays only"""
         L = _lib.lib()
         if inner is None:
             inner = [n for n in range(self.nblocks) if not any(self.blocks_host[n].bc[f] != 0 for f in range(2 * self.ndim))]
         mask = np.zeros(self.nblocks * self.ncell, dtype=np.uint8)
         zones = np.zeros(self.nblocks * self.ncell, dtype=np.uint32)
-        seg = (C.c_longlong * 6)()
+        seg = (C.c_longlong * 4)()
         nint = self.nx[0] * (self.nx[1] if self.ndim >= 2 else 1) * (self.nx[2] if self.ndim >= 3 else 1)
         pairs = np.zeros((self.nblocks * (self.ncell - nint), 2), dtype=np.uint32)
         pseg = (C.c_longlong * 3)()
@@ -311,14 +311,14 @@ class MeshPack:
         _lib.check(L.pb_ghost_plan_host(C.byref(cfg), C.addressof(self.blocks_host), self.nblocks, self.geom_host.ctypes.data,
                                         self.floor_host.ctypes.data, inn.ctypes.data if len(inner) else None, len(inner),
                                         mask.ctypes.data, zones.ctypes.data, seg, pairs.ctypes.data, pseg), "pb_ghost_plan_host")
-        return mask, zones[:seg[5]].copy(), tuple(seg), pairs[:pseg[2]].copy(), tuple(pseg)
+        return mask, zones[:seg[3]].copy(), tuple(seg), pairs[:pseg[2]].copy(), tuple(pseg)
 
     def _ghost_plan(self, pk, inner):
         """which ghost zones take their con2prim result from the same-GPU neighbour instead of solving again
         (pb_ghost_plan_host, csrc/ghost_plan_host.cpp); use_ghost_plan=False leaves the pack without a plan"""
         t = self.torch
         self.ghost_mask = self.c2p_zones = None
-        self.c2p_seg, self.n_deferred = (0,) * 6, 0
+        self.c2p_seg, self.n_deferred = (0, 0, 0, 0), 0
         if not self.use_ghost_plan or not self.p.bc_prim:
             return
         mask, zones, seg, pairs, pseg = self.ghost_plan_host(inner)
@@ -330,7 +330,7 @@ class MeshPack:
         self.c2p_zones = t.from_numpy(zones).to(self.device)
         pk.ghost_mask = self.ghost_mask.data_ptr()
         pk.c2p_zones = self.c2p_zones.data_ptr()
-        for n in range(6):
+        for n in range(4):
             pk.c2p_seg[n] = seg[n]
         self.halo_pairs = t.from_numpy(pairs).to(self.device)
         pk.halo_pairs = self.halo_pairs.data_ptr()

@@ -40,7 +40,7 @@ def test_plan_is_a_partition_and_respects_the_conditions(name):
     ncell = mesh.ncell
     tot = mesh.nblocks * ncell
     # zone list + deferred zones = every zone exactly once
-    assert seg[0] == 0 and seg[5] == len(zones) and all(seg[n] <= seg[n + 1] for n in range(5))
+    assert seg[0] == 0 and seg[3] == len(zones) and seg[1] <= seg[2] <= seg[3]
     seen = np.zeros(tot, dtype=np.int32)
     np.add.at(seen, zones.astype(np.int64), 1)
     assert np.array_equal(seen + mask.reshape(-1), np.ones(tot, dtype=np.int32))
@@ -65,22 +65,11 @@ def test_plan_is_a_partition_and_respects_the_conditions(name):
     inner = [n for n in range(mesh.nblocks) if not any(mesh.blocks_host[n].bc[f] != 0 for f in range(2 * mesh.ndim))]
     zb = zones.astype(np.int64) // ncell
     zc = zones.astype(np.int64) % ncell
-    # segments: rind of the inner blocks | their solved ghosts | rind + solved ghosts of the others | their cores | inner cores
-    ng = mesh.ng
-    kk, jj, ii = np.meshgrid(np.arange(mesh.shape[0]), np.arange(mesh.shape[1]), np.arange(mesh.shape[2]), indexing="ij")
-    core = np.ones(mesh.shape, dtype=bool)
-    for d, c in enumerate((ii, jj, kk)):
-        if d < mesh.ndim:
-            core &= (c >= 2 * ng) & (c < ng + mesh.nx[d] - ng)
-    core, gh = core.reshape(-1), ghost.reshape(-1)
-    S = [slice(seg[n], seg[n + 1]) for n in range(5)]
-    assert set(zb[S[0]]) <= set(inner) and not gh[zc[S[0]]].any() and not core[zc[S[0]]].any()
-    assert set(zb[S[1]]) <= set(inner) and gh[zc[S[1]]].all()
-    assert not (set(zb[S[2]]) & set(inner)) and not core[zc[S[2]]].any()
-    assert not (set(zb[S[3]]) & set(inner)) and core[zc[S[3]]].all()
-    assert set(zb[S[4]]) <= set(inner) and core[zc[S[4]]].all()
-    # every zone a ghost copy reads lies in segments 0-2 (the copy of the deferred zones runs beside segments 3-4)
-    assert not core[mesh.plan_pairs[:, 1].astype(np.int64) % ncell].any()
+    # segments: interiors of the inner blocks | their other zones | the other blocks
+    assert set(zb[:seg[1]]) <= set(inner) and not ghost.reshape(-1)[zc[:seg[1]]].any()
+    assert set(zb[seg[1]:seg[2]]) <= set(inner) and ghost.reshape(-1)[zc[seg[1]:seg[2]]].all()
+    assert not (set(zb[seg[2]:]) & set(inner))
+    assert seg[1] == len(inner) * mesh.nx[0] * mesh.nx[1] * mesh.nx[2] if mesh.ndim == 3 else True
     for n in range(mesh.nblocks):
         blk = mesh.blocks_host[n]
         m = mask[n].astype(bool)

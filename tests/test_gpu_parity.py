@@ -696,7 +696,7 @@ def test_con2prim_variants_bit_identical_and_statistics(name):
             out[mode] = {k: _np(getattr(mesh, k)).copy() for k in FIELDS}
             out[mode]["cons"] = _np(mesh.cons["base"]).copy()
             # with the ghost plan only the plan's zone list is solved (the deferred ghost zones copy the neighbour's result)
-            nstage, ncells = len(stage_tags(g)), (mesh.c2p_seg[5] if mesh.ghost_mask is not None else mesh.nblocks * mesh.ncell)
+            nstage, ncells = len(stage_tags(g)), (mesh.c2p_seg[3] if mesh.ghost_mask is not None else mesh.nblocks * mesh.ncell)
     finally:
         L.pb_set_option(b"c2p_arith", 2)
     for mode in (2, 0):
@@ -821,21 +821,16 @@ def _torus_run(block, mesh_nx, cycles, use_ghost_plan, force_split=False, graphs
     return out, mesh
 
 
-@pytest.mark.parametrize("force_split,overlap", [(False, 1), (True, 1), (False, 0)])
-def test_ghost_plan_on_a_mesh_with_inner_blocks_changes_no_bit(force_split, overlap):
+@pytest.mark.parametrize("force_split", [False, True])
+def test_ghost_plan_on_a_mesh_with_inner_blocks_changes_no_bit(force_split):
     """64 MeshBlocks of 16^3 (8 of them away from every mesh boundary, so all three segments of the plan's zone list are
     populated): two cycles with the ghost plan equal two cycles without it in every field of every zone, ghosts
     included, and in the floor / failure counters; also with con2prim split around the (here empty) transfer"""
-    from phoebus_b200 import _lib
     ref, mref = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=False)
-    try:
-        _lib.lib().pb_set_option(b"halo_overlap", overlap)  # deferred copy beside the con2prim of the block cores, or after it
-        out, mesh = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=True, force_split=force_split)
-    finally:
-        _lib.lib().pb_set_option(b"halo_overlap", 1)
+    out, mesh = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=True, force_split=force_split)
     assert mref.ghost_mask is None and mesh.ghost_mask is not None
     seg = mesh.c2p_seg
-    assert 0 < seg[1] < seg[2] < seg[3] < seg[4] < seg[5] < mesh.nblocks * mesh.ncell
+    assert 0 < seg[1] < seg[2] < seg[3] < mesh.nblocks * mesh.ncell
     assert mesh.n_deferred > 0.2 * mesh.nblocks * mesh.ncell
     for k in ref:
         assert np.array_equal(out[k], ref[k], equal_nan=True), k
