@@ -125,19 +125,16 @@ typedef struct pb_pack {
   const unsigned char *ghost_mask; /* device [b][cells]: 1 = deferred ghost zone */
   const unsigned *c2p_zones;       /* device [c2p_seg[3]]: zone ids b * cells + cell, three segments */
   long long c2p_seg[4];            /* 0 | interiors of inner_blocks | their other zones | zones of the other blocks */
-  const unsigned *halo_pairs;      /* device [halo_seg[2]][2]: (destination, source) zone ids of the same-pack ghost copies; */
-  long long halo_seg[3];           /* 0 | copied before con2prim | the deferred zones, copied after it */
 } pb_pack_t;
 
 /* Host-side construction of the ghost plan (ghost_plan_host.cpp states the conditions). blocks / geom_host / floor_host
  * are the HOST copies of what the pack holds on the device; inner_blocks may be NULL (then segments 0 and 1 are empty).
- * mask_out: nblocks * cells bytes; zones_out: room for nblocks * cells entries; seg_out as pb_pack_t.c2p_seg; pairs_out
- * (optional, with pair_seg_out as pb_pack_t.halo_seg): room for 2 * nblocks * (cells - interior cells) entries. The caller
+ * mask_out: nblocks * cells bytes; zones_out: room for nblocks * cells entries; seg_out as pb_pack_t.c2p_seg. The caller
  * uploads both. Returns PB_OK; a configuration the shortcut does not apply to (bc_vars = conserved, floor type RRhoSie)
  * yields an all-zero mask and the full zone list. */
 int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks, int nblocks, const double *geom_host,
                        const double *floor_host, const int *inner_blocks, int n_inner, unsigned char *mask_out,
-                       unsigned *zones_out, long long seg_out[4], unsigned *pairs_out, long long pair_seg_out[3]);
+                       unsigned *zones_out, long long seg_out[4]);
 /* Same-GPU ghost copy with the plan: phase 0 = every ghost zone (pb_halo_exchange_local); 1 = all but the deferred zones;
  * 2 = only the deferred zones, every field con2prim reads or writes (conserved, primitives, temperature, c2p_mu, fail,
  * cell signal speeds, zone flags), to be called after con2prim and before the fixup. */

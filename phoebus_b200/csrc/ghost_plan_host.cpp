@@ -49,8 +49,7 @@ inline bool same_bits(double a, double b) { return std::memcmp(&a, &b, sizeof(do
 
 extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks, int nblocks, const double *geom_host,
                                   const double *floor_host, const int *inner_blocks, int n_inner,
-                                  unsigned char *mask_out, unsigned *zones_out, long long seg_out[4],
-                                  unsigned *pairs_out, long long pair_seg_out[3]) {
+                                  unsigned char *mask_out, unsigned *zones_out, long long seg_out[4]) {
   if (!cfg || !blocks || nblocks <= 0 || !geom_host || !floor_host || !mask_out || !zones_out || !seg_out) return PB_EINVAL;
   const HostLay L(*cfg);
   if ((long long)nblocks * L.ncell >= (1ll << 32)) return PB_EINVAL;
@@ -126,31 +125,6 @@ extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks,
           }
     }
     seg_out[pass + 1] = n;
-  }
-  // (destination, source) zone ids of the same-pack ghost copies: the zones copied before con2prim, then the deferred ones
-  if (pairs_out && pair_seg_out) {
-    long long m = 0;
-    pair_seg_out[0] = 0;
-    for (int phase = 1; phase <= 2; ++phase) {
-      for (int b = 0; b < nblocks; ++b) {
-        const pb_block_t &blk = blocks[b];
-        for (int k = 0; k < L.nk; ++k)
-          for (int j = 0; j < L.nj; ++j)
-            for (int i = 0; i < L.ni; ++i) {
-              if (interior(k, j, i)) continue;
-              const size_t z = (size_t)b * L.ncell + L.idx(k, j, i);
-              if ((mask_out[z] != 0) != (phase == 2)) continue;
-              const int o1 = i < L.lo[0] ? -1 : (i > L.hi[0] ? 1 : 0), o2 = j < L.lo[1] ? -1 : (j > L.hi[1] ? 1 : 0),
-                        o3 = k < L.lo[2] ? -1 : (k > L.hi[2] ? 1 : 0);
-              const int nb = blk.nbr[(o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)];
-              if (nb < 0 || nb >= nblocks) continue;
-              pairs_out[2 * m] = (unsigned)z;
-              pairs_out[2 * m + 1] = (unsigned)((size_t)nb * L.ncell + L.idx(k - o3 * nx[2], j - o2 * nx[1], i - o1 * nx[0]));
-              ++m;
-            }
-      }
-      pair_seg_out[phase] = m;
-    }
   }
   return PB_OK;
 }

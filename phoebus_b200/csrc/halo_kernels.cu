@@ -38,91 +38,67 @@ static HaloFields halo_fields(const pb_pack_t &pack, const pb_cfg_t &cfg, Real *
   return f;
 }
 
-// Copy of one ghost zone (T = double) or of two zones adjacent along x1 (T = double2; offsets even): all components of a
-// field group are loaded before any is stored — source and destination live in the same arrays, so the compiler cannot
-// hoist loads over stores by itself, and a zone's 8 (conserved) or 8 + 13 (with bc_vars = primitive) words would
-// otherwise be that many serial DRAM round trips. HOIST: one group for everything (more registers, one round trip).
-template <class T, bool MHD, bool PRIM, int PHASE, bool HOIST>
+// Copy of one ghost zone: all components of a field group are loaded before any is stored — source and destination live
+// in the same arrays, so the compiler cannot hoist loads over stores by itself, and a zone's 8 (conserved) or 8 + 13 (with
+// bc_vars = primitive) words would otherwise be that many serial DRAM round trips (measured: 1.63 -> 1.31 ms per exchange
+// at 256^3). Measured and dropped (profiles/r02i_variants_halo_mapping.txt, r02j, r02n): one load group for everything, 16-byte
+// accesses for pairs of zones, a precomputed (destination, source) list instead of the index decoding, higher occupancy —
+// the copy is bound by the memory system (128-byte line fills for 32-byte row ends), not by instructions or latency.
+template <bool MHD, bool PRIM, int PHASE>
 PB_DEV void halo_copy_zone(const pb_pack_t &pack, const HaloFields &hf, const int ndim, const int N, const size_t b, const size_t nb,
                            const int o, const int so) {
   constexpr int NCn = NC<MHD>::ncons, NP = NC<MHD>::nprim;
-  auto at = [](Real *p) { return reinterpret_cast<T *>(p); };
-  T *csrc = at(hf.ptr[0] + nb * NCn * N + so), *cdst = at(hf.ptr[0] + b * NCn * N + o);
-  constexpr int S = sizeof(T) / sizeof(Real);
-  const size_t NS = (size_t)N / S; // component stride in units of T
-  T v[NCn], q[PRIM ? NP : 1], w[3], c[3];
+  {
+    const Real *src = hf.ptr[0] + nb * NCn * N + so;
+    Real *dst = hf.ptr[0] + b * NCn * N + o;
+    Real v[NCn];
 #pragma unroll
-  for (int n = 0; n < NCn; ++n) v[n] = csrc[n * NS];
-  if (!HOIST) {
+    for (int n = 0; n < NCn; ++n) v[n] = src[(size_t)n * N];
 #pragma unroll
-    for (int n = 0; n < NCn; ++n) cdst[n * NS] = v[n];
+    for (int n = 0; n < NCn; ++n) dst[(size_t)n * N] = v[n];
   }
   if (PRIM) {
-    T *src = at(hf.ptr[1] + nb * NP * N + so), *dst = at(hf.ptr[1] + b * NP * N + o);
+    const Real *src = hf.ptr[1] + nb * NP * N + so;
+    Real *dst = hf.ptr[1] + b * NP * N + o;
+    Real q[NP], w[3];
 #pragma unroll
-    for (int n = 0; n < NP; ++n) q[n] = src[n * NS];
+    for (int n = 0; n < NP; ++n) q[n] = src[(size_t)n * N];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) w[f] = *at(hf.ptr[2 + f] + nb * N + so);
-    if (PHASE == 2 && HOIST) {
+    for (int f = 0; f < 3; ++f) w[f] = hf.ptr[2 + f][nb * N + so];
 #pragma unroll
-      for (int d = 0; d < 3; ++d)
-        if (d < ndim) c[d] = *at(pack.csig + (nb * ndim + d) * N + so);
-    }
-    if (HOIST) {
+    for (int n = 0; n < NP; ++n) dst[(size_t)n * N] = q[n];
 #pragma unroll
-      for (int n = 0; n < NCn; ++n) cdst[n * NS] = v[n];
-    }
-#pragma unroll
-    for (int n = 0; n < NP; ++n) dst[n * NS] = q[n];
-#pragma unroll
-    for (int f = 0; f < 3; ++f) *at(hf.ptr[2 + f] + b * N + o) = w[f];
-  } else if (HOIST) {
-#pragma unroll
-    for (int n = 0; n < NCn; ++n) cdst[n * NS] = v[n];
+    for (int f = 0; f < 3; ++f) hf.ptr[2 + f][b * N + o] = w[f];
   }
   if (PHASE == 2) {
-    if (!(PRIM && HOIST)) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-        if (d < ndim) c[d] = *at(pack.csig + (nb * ndim + d) * N + so);
-    }
+    Real c[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d)
-      if (d < ndim) *at(pack.csig + (b * ndim + d) * N + o) = c[d];
-    if (pack.zflags) {
-      for (int u = 0; u < S; ++u) pack.zflags[b * N + o + u] = pack.zflags[nb * N + so + u];
-    }
+      if (d < ndim) c[d] = pack.csig[(nb * ndim + d) * N + so];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (d < ndim) pack.csig[(b * ndim + d) * N + o] = c[d];
+    if (pack.zflags) pack.zflags[b * N + o] = pack.zflags[nb * N + so];
   }
 }
 
+// One thread per ghost zone (Shell enumeration: rows along x1 stay contiguous).
 // PHASE (ghost plan, ghost_plan_host.cpp): 0 every ghost zone; 1 skip the zones flagged in pack.ghost_mask; 2 only
 // those, after con2prim, with the cell signal speeds and the zone flags on top of the exchanged fields.
-// VAR 0: one thread per ghost zone; 1: the same with a single load group; 2: one thread per pair of zones adjacent along
-// x1 (16-byte accesses; needs even nx1 and ng — ghost / interior boundaries then fall between pairs).
-template <bool MHD, bool PRIM, int PHASE, int VAR>
+template <bool MHD, bool PRIM, int PHASE>
 __global__ void __launch_bounds__(256) halo_local_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const HaloFields hf) {
   const Lay L(cfg);
-  Lay Lh = L;
-  if (VAR == 2) {
-    Lh.ni = L.ni / 2;
-    Lh.is = L.is / 2;
-    Lh.ie = (L.ie + 1) / 2 - 1;
-  }
-  const Shell sh(Lh);
+  const Shell sh(L);
   const int N = L.ncell;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)sh.n * pack.nblocks) return;
   const int b = (int)(t / sh.n);
   int i, j, k;
-  sh.cell(Lh, (int)(t % sh.n), k, j, i);
-  if (VAR == 2) i *= 2;
+  sh.cell(L, (int)(t % sh.n), k, j, i);
   const int o = L.idx(k, j, i);
-  bool first = true, second = VAR == 2;
   if (PHASE != 0) {
-    const unsigned char *m = pack.ghost_mask + (size_t)b * N + o;
-    first = (m[0] != 0) == (PHASE == 2);
-    if (VAR == 2) second = (m[1] != 0) == (PHASE == 2);
-    if (!first && !second) return;
+    const bool deferred = pack.ghost_mask[(size_t)b * N + o] != 0;
+    if (deferred != (PHASE == 2)) return;
   }
   const int o1 = i < L.is ? -1 : (i > L.ie ? 1 : 0);
   const int o2 = j < L.js ? -1 : (j > L.je ? 1 : 0);
@@ -131,27 +107,7 @@ __global__ void __launch_bounds__(256) halo_local_kernel(const pb_pack_t pack, c
   const int nb = pack.blocks[b].nbr[(o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)];
   if (nb < 0) return;
   const int si = i - o1 * cfg.nx[0], sj = j - o2 * cfg.nx[1], sk = k - o3 * cfg.nx[2];
-  const int so = L.idx(sk, sj, si);
-  if (VAR == 2) {
-    if (first && second) halo_copy_zone<double2, MHD, PRIM, PHASE, false>(pack, hf, L.ndim, N, b, nb, o, so);
-    else halo_copy_zone<double, MHD, PRIM, PHASE, false>(pack, hf, L.ndim, N, b, nb, o + (second ? 1 : 0), so + (second ? 1 : 0));
-  } else {
-    halo_copy_zone<double, MHD, PRIM, PHASE, VAR == 1>(pack, hf, L.ndim, N, b, nb, o, so);
-  }
-}
-
-// The same copy driven by the ghost plan's (destination, source) list: no index decoding, no idle lanes — the two phases
-// of a planned stage each visit only their own zones.
-template <bool MHD, bool PRIM, int PHASE>
-__global__ void __launch_bounds__(256) halo_list_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const HaloFields hf,
-                                                        const uint2 *__restrict__ pairs, const long long n) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n) return;
-  const Lay L(cfg);
-  const unsigned N = (unsigned)L.ncell;
-  const uint2 p = __ldg(pairs + t);
-  const unsigned b = p.x / N, nb = p.y / N;
-  halo_copy_zone<double, MHD, PRIM, PHASE, false>(pack, hf, L.ndim, (int)N, b, nb, (int)(p.x - b * N), (int)(p.y - nb * N));
+  halo_copy_zone<MHD, PRIM, PHASE>(pack, hf, L.ndim, N, b, nb, o, L.idx(sk, sj, si));
 }
 
 // plan entry: {block, i0, i1, j0, j1, k0, k1, off_lo, off_hi, reserved}; offset in doubles
@@ -212,63 +168,18 @@ extern "C" int pb_halo_exchange_local_ex(const pb_pack_t *pack, const pb_cfg_t *
   if (phase == 2 && !cfg->bc_prim) return PB_OK; // no zone is ever deferred without bc_vars = primitive
   if (phase == 2) PB_NEED("pb_halo_exchange_local_ex", PB_F(pack, csig));
   const Lay L(*cfg);
-  static const bool use_list = [] {
-    const char *e = getenv("PB_HALO_LIST");
-    return !(e && e[0] == '0');
-  }();
-  if (phase != 0 && pack->halo_pairs && use_list) {
-    const long long n = pack->halo_seg[phase] - pack->halo_seg[phase - 1];
-    if (n <= 0) return PB_OK;
-    const uint2 *pairs = reinterpret_cast<const uint2 *>(pack->halo_pairs) + pack->halo_seg[phase - 1];
-    const unsigned G = (unsigned)((n + 255) / 256);
-    const HaloFields hf = halo_fields(*pack, *cfg, cons);
-    cudaStream_t st = (cudaStream_t)stream;
-#define PB_HALO_L(M, P)                                                                          \
-  do {                                                                                           \
-    if (phase == 1) halo_list_kernel<M, P, 1><<<G, 256, 0, st>>>(*pack, *cfg, hf, pairs, n);     \
-    else halo_list_kernel<M, P, 2><<<G, 256, 0, st>>>(*pack, *cfg, hf, pairs, n);                \
-  } while (0)
-    if (cfg->mhd) {
-      if (cfg->bc_prim) PB_HALO_L(true, true);
-      else PB_HALO_L(true, false);
-    } else {
-      if (cfg->bc_prim) PB_HALO_L(false, true);
-      else PB_HALO_L(false, false);
-    }
-#undef PB_HALO_L
-    return check_launch("halo_list_kernel");
-  }
-  // thread mapping: PB_HALO_VARIANT=zone|hoist|pair (default zone: the three measured the same, profiles/r02i_variants.txt)
-  static const int want = [] {
-    const char *e = getenv("PB_HALO_VARIANT");
-    return (e && e[0] == 'p') ? 2 : ((e && e[0] == 'h') ? 1 : 0);
-  }();
-  const bool pairs_ok = cfg->nx[0] % 2 == 0 && cfg->ng % 2 == 0 && L.ncell % 2 == 0;
-  const int var = (want == 2 && !pairs_ok) ? 0 : want;
-  Lay Lh = L;
-  if (var == 2) {
-    Lh.ni = L.ni / 2;
-    Lh.is = L.is / 2;
-    Lh.ie = (L.ie + 1) / 2 - 1;
-  }
-  const Shell sh(Lh);
+  const Shell sh(L);
   const long long n = (long long)sh.n * pack->nblocks;
   if (n <= 0) return PB_OK;
   const int T = 256;
   const unsigned G = (unsigned)((n + T - 1) / T);
   const HaloFields hf = halo_fields(*pack, *cfg, cons);
   cudaStream_t st = (cudaStream_t)stream;
-#define PB_HALO_V(M, P, PH)                                                              \
-  do {                                                                                   \
-    if (var == 0) halo_local_kernel<M, P, PH, 0><<<G, T, 0, st>>>(*pack, *cfg, hf);      \
-    else if (var == 1) halo_local_kernel<M, P, PH, 1><<<G, T, 0, st>>>(*pack, *cfg, hf); \
-    else halo_local_kernel<M, P, PH, 2><<<G, T, 0, st>>>(*pack, *cfg, hf);               \
-  } while (0)
-#define PB_HALO(M, P)                        \
-  do {                                       \
-    if (phase == 0) PB_HALO_V(M, P, 0);      \
-    else if (phase == 1) PB_HALO_V(M, P, 1); \
-    else PB_HALO_V(M, P, 2);                 \
+#define PB_HALO(M, P)                                                                   \
+  do {                                                                                  \
+    if (phase == 0) halo_local_kernel<M, P, 0><<<G, T, 0, st>>>(*pack, *cfg, hf);       \
+    else if (phase == 1) halo_local_kernel<M, P, 1><<<G, T, 0, st>>>(*pack, *cfg, hf);  \
+    else halo_local_kernel<M, P, 2><<<G, T, 0, st>>>(*pack, *cfg, hf);                  \
   } while (0)
   if (cfg->mhd) {
     if (cfg->bc_prim) PB_HALO(true, true);
@@ -278,7 +189,6 @@ extern "C" int pb_halo_exchange_local_ex(const pb_pack_t *pack, const pb_cfg_t *
     else PB_HALO(false, false);
   }
 #undef PB_HALO
-#undef PB_HALO_V
   return check_launch("halo_local_kernel");
 }
 

@@ -738,17 +738,13 @@ void Mesh::Allocate() {
   // ghost plan: ghost zones whose con2prim result is copied from the same-GPU neighbour (include/phoebus_b200.h)
   pack_.ghost_mask = nullptr;
   pack_.c2p_zones = nullptr;
-  pack_.halo_pairs = nullptr;
   for (int n = 0; n < 4; ++n) pack_.c2p_seg[n] = 0;
-  for (int n = 0; n < 3; ++n) pack_.halo_seg[n] = 0;
   if (cfg.bc_prim) {
     std::vector<unsigned char> mask((size_t)nblocks * cells);
     std::vector<unsigned> zones((size_t)nblocks * cells);
-    long long seg[4], pseg[3];
-    std::vector<unsigned> pairs((size_t)2 * nblocks * cells);
+    long long seg[4];
     CheckPb(pb_ghost_plan_host(&cfg, blocks_host.data(), nblocks, geom_host_.data(), floor_host_.data(),
-                               inner.empty() ? nullptr : inner.data(), (int)inner.size(), mask.data(), zones.data(), seg,
-                               pairs.data(), pseg),
+                               inner.empty() ? nullptr : inner.data(), (int)inner.size(), mask.data(), zones.data(), seg),
             "pb_ghost_plan_host");
     if (seg[3] < (long long)nblocks * cells) {
       unsigned char *mask_dev = (unsigned char *)dev(mask.size());
@@ -758,10 +754,6 @@ void Mesh::Allocate() {
       pack_.ghost_mask = mask_dev;
       pack_.c2p_zones = zones_dev;
       for (int n = 0; n < 4; ++n) pack_.c2p_seg[n] = seg[n];
-      unsigned *pairs_dev = (unsigned *)dev(sizeof(unsigned) * 2 * (size_t)std::max<long long>(1, pseg[2]));
-      CheckCuda(cudaMemcpy(pairs_dev, pairs.data(), sizeof(unsigned) * 2 * (size_t)pseg[2], cudaMemcpyHostToDevice), "halo pair list H2D");
-      pack_.halo_pairs = pairs_dev;
-      for (int n = 0; n < 3; ++n) pack_.halo_seg[n] = pseg[n];
     }
   }
   AddContainer("base");
@@ -831,7 +823,6 @@ std::shared_ptr<MeshBlockData<Real>> Mesh::GetBlockData(int b, const std::string
   p.n_inner_blocks = 0;
   p.ghost_mask = nullptr; // the plan describes the whole pack
   p.c2p_zones = nullptr;
-  p.halo_pairs = nullptr;
   rc->pack = p;
   rc->cons = cons_[stage] + o * (stage == "geometric source terms" ? 4 : ncons);
   return rc;

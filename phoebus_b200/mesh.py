@@ -295,23 +295,19 @@ class MeshPack:
         self.flags_valid = False
 
     def ghost_plan_host(self, inner=None):
-        """(mask [nblocks*ncell] u8, zones u32, seg[4], pairs u32 [n][2], pair_seg[3]) of pb_ghost_plan_host for this
-        pack — host arrays only"""
+        """(mask [nblocks*ncell] u8, zones u32, seg[4]) of pb_ghost_plan_host for this pack — host arrays only"""
         L = _lib.lib()
         if inner is None:
             inner = [n for n in range(self.nblocks) if not any(self.blocks_host[n].bc[f] != 0 for f in range(2 * self.ndim))]
         mask = np.zeros(self.nblocks * self.ncell, dtype=np.uint8)
         zones = np.zeros(self.nblocks * self.ncell, dtype=np.uint32)
         seg = (C.c_longlong * 4)()
-        nint = self.nx[0] * (self.nx[1] if self.ndim >= 2 else 1) * (self.nx[2] if self.ndim >= 3 else 1)
-        pairs = np.zeros((self.nblocks * (self.ncell - nint), 2), dtype=np.uint32)
-        pseg = (C.c_longlong * 3)()
         inn = np.ascontiguousarray(inner, dtype=np.int32)
         cfg = self.p.make_cfg(self.gshape)
         _lib.check(L.pb_ghost_plan_host(C.byref(cfg), C.addressof(self.blocks_host), self.nblocks, self.geom_host.ctypes.data,
                                         self.floor_host.ctypes.data, inn.ctypes.data if len(inner) else None, len(inner),
-                                        mask.ctypes.data, zones.ctypes.data, seg, pairs.ctypes.data, pseg), "pb_ghost_plan_host")
-        return mask, zones[:seg[3]].copy(), tuple(seg), pairs[:pseg[2]].copy(), tuple(pseg)
+                                        mask.ctypes.data, zones.ctypes.data, seg), "pb_ghost_plan_host")
+        return mask, zones[:seg[3]].copy(), tuple(seg)
 
     def _ghost_plan(self, pk, inner):
         """which ghost zones take their con2prim result from the same-GPU neighbour instead of solving again
@@ -321,7 +317,7 @@ class MeshPack:
         self.c2p_seg, self.n_deferred = (0, 0, 0, 0), 0
         if not self.use_ghost_plan or not self.p.bc_prim:
             return
-        mask, zones, seg, pairs, pseg = self.ghost_plan_host(inner)
+        mask, zones, seg = self.ghost_plan_host(inner)
         self.c2p_seg = seg
         self.n_deferred = int(mask.sum())
         if self.n_deferred == 0:
@@ -332,10 +328,6 @@ class MeshPack:
         pk.c2p_zones = self.c2p_zones.data_ptr()
         for n in range(4):
             pk.c2p_seg[n] = seg[n]
-        self.halo_pairs = t.from_numpy(pairs).to(self.device)
-        pk.halo_pairs = self.halo_pairs.data_ptr()
-        for n in range(3):
-            pk.halo_seg[n] = pseg[n]
 
     def zones(self):
         """interior zones owned by this pack"""
