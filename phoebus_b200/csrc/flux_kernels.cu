@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstring>
 
+#define PB_FLOORS_OUT_OF_LINE 1 // see get_floors (pb_device.cuh)
 #include "pb_device.cuh"
 #include "pb_host.hpp"
 

@@ -8,6 +8,7 @@
 // fused, the whole kernel runs at the Riemann solve's occupancy (17 warps/SM, FP64 pipe 50 % busy).
 // Split, reconstruction runs at 2-3x the occupancy; the ql/qr round trip (40 words per zone and
 // direction) hides under the arithmetic (measured: profiles/r01_flux_split*.md).
+#define PB_FLOORS_OUT_OF_LINE 1 // see get_floors (pb_device.cuh)
 #include "pb_device.cuh"
 #include "pb_host.hpp"
 
