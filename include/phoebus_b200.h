@@ -118,23 +118,21 @@ typedef struct pb_pack {
                              * reference's ql / qr fields, ref: src/fluid/fluid.cpp:288-299). When present,
                              * pb_calculate_fluxes runs reconstruction and Riemann solve as two launches per
                              * direction (higher occupancy for the reconstruction); NULL: one fused launch */
-  /* optional ghost plan (pb_ghost_plan_host; all three or none). The stage sequencer then solves con2prim only on
-   * c2p_zones and fills the ghost zones flagged in ghost_mask from the interior zone of their same-pack neighbour AFTER
-   * con2prim: the reference solves those zones twice with identical inputs and tables (ghost_plan_host.cpp). The
-   * task-level entry points (pb_cons_to_prim, pb_halo_exchange_local, ...) ignore the plan. */
+  /* optional ghost plan (pb_ghost_plan_host; all or none). The stage sequencer then solves con2prim only on the interior
+   * zones and on the ghost zones listed in c2p_zones, and fills the ghost zones flagged in ghost_mask from the interior
+   * zone of their same-pack neighbour AFTER con2prim: the reference solves those zones twice with identical inputs and
+   * tables (ghost_plan_host.cpp). The task-level entry points (pb_cons_to_prim, pb_halo_exchange_local, ...) ignore it. */
   const unsigned char *ghost_mask; /* device [b][cells]: 1 = deferred ghost zone */
-  const unsigned *c2p_zones;       /* device [c2p_seg[3]]: zone ids b * cells + cell, three segments */
-  long long c2p_seg[4];            /* 0 | interiors of inner_blocks | their other zones | zones of the other blocks */
+  const unsigned *c2p_zones;       /* device [n_c2p_zones]: ids b * cells + cell of the ghost zones that are solved */
+  long long n_c2p_zones;
 } pb_pack_t;
 
 /* Host-side construction of the ghost plan (ghost_plan_host.cpp states the conditions). blocks / geom_host / floor_host
- * are the HOST copies of what the pack holds on the device; inner_blocks may be NULL (then segments 0 and 1 are empty).
- * mask_out: nblocks * cells bytes; zones_out: room for nblocks * cells entries; seg_out as pb_pack_t.c2p_seg. The caller
- * uploads both. Returns PB_OK; a configuration the shortcut does not apply to (bc_vars = conserved, floor type RRhoSie)
- * yields an all-zero mask and the full zone list. */
+ * are the HOST copies of what the pack holds on the device. mask_out: nblocks * cells bytes; zones_out: room for nblocks *
+ * (cells - interior cells) entries, *nzones_out of them written. The caller uploads both. Returns PB_OK; a configuration the
+ * shortcut does not apply to (bc_vars = conserved, floor type RRhoSie) yields an all-zero mask and every ghost zone listed. */
 int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks, int nblocks, const double *geom_host,
-                       const double *floor_host, const int *inner_blocks, int n_inner, unsigned char *mask_out,
-                       unsigned *zones_out, long long seg_out[4]);
+                       const double *floor_host, unsigned char *mask_out, unsigned *zones_out, long long *nzones_out);
 /* Same-GPU ghost copy with the plan: phase 0 = every ghost zone (pb_halo_exchange_local); 1 = all but the deferred zones;
  * 2 = only the deferred zones, every field con2prim reads or writes (conserved, primitives, temperature, c2p_mu, fail,
  * cell signal speeds, zone flags), to be called after con2prim and before the fixup. */

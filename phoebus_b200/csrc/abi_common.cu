@@ -288,8 +288,8 @@ int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const i
                unsigned char *zflags, cudaStream_t s);
 int launch_c2p_list(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, int which,
                     unsigned char *zflags, cudaStream_t s);
-int launch_c2p_zones(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, long long from, long long to,
-                     unsigned char *zflags, cudaStream_t s);
+int launch_c2p_plan(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, bool with_ghosts,
+                    unsigned char *zflags, cudaStream_t s);
 int launch_fixup(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, int mode, unsigned char *zflags, cudaStream_t s);
 int launch_floors(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, unsigned long long *counters, int mode,
                   unsigned char *zflags, const double *lazy_u0, const double *lazy_ubase, double beta, cudaStream_t s);
@@ -358,7 +358,7 @@ extern "C" int pb_early_c2p_pays(const pb_pack_t *pack) {
 // themselves (inter-GPU exchange) pass phase = pb_ghost_plan_active(...) to pb_halo_exchange_local_ex.
 extern "C" int pb_ghost_plan_active(const pb_pack_t *pack, const pb_cfg_t *cfg) {
   if (!pack || !cfg || !g_ghost_plan || !cfg->bc_prim) return 0;
-  return (pack->ghost_mask && pack->c2p_zones && pack->c2p_seg[3] > 0) ? 1 : 0;
+  return (pack->ghost_mask && pack->c2p_zones) ? 1 : 0;
 }
 
 extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg, double *sc1, void *stream) {
@@ -369,7 +369,7 @@ extern "C" int pb_rk_stage_post_early(const pb_pack_t *pack, const pb_cfg_t *cfg
     return set_error(PB_EINVAL, "pb_rk_stage_post_early: inner_blocks and bc_blocks must partition the pack");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope p(PB_TASK_C2P, s);
-  if (pb_ghost_plan_active(pack, cfg)) return launch_c2p_zones(pack, cfg, sc1, pack->c2p_seg[0], pack->c2p_seg[1], pack->zflags, s);
+  if (pb_ghost_plan_active(pack, cfg)) return launch_c2p_plan(pack, cfg, sc1, pack->inner_blocks, pack->n_inner_blocks, false, pack->zflags, s);
   return launch_c2p_list(pack, cfg, sc1, pack->inner_blocks, pack->n_inner_blocks, 0, pack->zflags, s);
 }
 
@@ -395,7 +395,9 @@ extern "C" int pb_rk_stage_post2(const pb_pack_t *pack, const pb_cfg_t *cfg, dou
     // which reads ghost primitives and fail flags as con2prim left them)
     {
       ProfScope p(PB_TASK_C2P, s);
-      if ((rc = launch_c2p_zones(pack, cfg, sc1, split ? pack->c2p_seg[1] : pack->c2p_seg[0], pack->c2p_seg[3], pack->zflags, s))) return rc;
+      if (split) rc = launch_c2p_plan(pack, cfg, sc1, pack->bc_blocks, pack->n_bc_blocks, true, pack->zflags, s);
+      else rc = launch_c2p_plan(pack, cfg, sc1, nullptr, pack->nblocks, true, pack->zflags, s);
+      if (rc) return rc;
     }
     ProfScope p(PB_TASK_HALO, s);
     if ((rc = pb_halo_exchange_local_ex(pack, cfg, sc1, 2, stream))) return rc;

@@ -21,7 +21,6 @@
 // fixture runs with the plan on and off).
 #include <cstdint>
 #include <cstring>
-#include <vector>
 
 #include "../../include/phoebus_b200.h"
 
@@ -48,9 +47,9 @@ inline bool same_bits(double a, double b) { return std::memcmp(&a, &b, sizeof(do
 } // namespace
 
 extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks, int nblocks, const double *geom_host,
-                                  const double *floor_host, const int *inner_blocks, int n_inner,
-                                  unsigned char *mask_out, unsigned *zones_out, long long seg_out[4]) {
-  if (!cfg || !blocks || nblocks <= 0 || !geom_host || !floor_host || !mask_out || !zones_out || !seg_out) return PB_EINVAL;
+                                  const double *floor_host, unsigned char *mask_out, unsigned *zones_out,
+                                  long long *nzones_out) {
+  if (!cfg || !blocks || nblocks <= 0 || !geom_host || !floor_host || !mask_out || !zones_out || !nzones_out) return PB_EINVAL;
   const HostLay L(*cfg);
   if ((long long)nblocks * L.ncell >= (1ll << 32)) return PB_EINVAL;
   const size_t gcell = (size_t)cfg->gk * cfg->gj * cfg->gi;
@@ -102,29 +101,18 @@ extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks,
           if (ok) mask_out[(size_t)b * L.ncell + L.idx(k, j, i)] = 1;
         }
   }
-  // zone list in three segments: interiors of the inner blocks | their remaining ghost zones | the other blocks
-  std::vector<char> inner(nblocks, 0);
-  for (int n = 0; n < n_inner && inner_blocks; ++n)
-    if (inner_blocks[n] >= 0 && inner_blocks[n] < nblocks) inner[inner_blocks[n]] = 1;
+  // the ghost zones that keep their own con2prim (interior zones are enumerated arithmetically by the kernels)
   long long n = 0;
-  seg_out[0] = 0;
-  auto interior = [&](int k, int j, int i) {
-    return i >= L.lo[0] && i <= L.hi[0] && j >= L.lo[1] && j <= L.hi[1] && k >= L.lo[2] && k <= L.hi[2];
-  };
-  for (int pass = 0; pass < 3; ++pass) {
-    for (int b = 0; b < nblocks; ++b) {
-      if ((pass < 2) != (inner[b] != 0)) continue;
-      const unsigned base = (unsigned)((size_t)b * L.ncell);
-      for (int k = 0; k < L.nk; ++k)
-        for (int j = 0; j < L.nj; ++j)
-          for (int i = 0; i < L.ni; ++i) {
-            const int o = L.idx(k, j, i);
-            if (mask_out[(size_t)base + o]) continue;
-            if (pass < 2 && (pass == 0) != interior(k, j, i)) continue;
-            zones_out[n++] = base + (unsigned)o;
-          }
-    }
-    seg_out[pass + 1] = n;
+  for (int b = 0; b < nblocks; ++b) {
+    const unsigned base = (unsigned)((size_t)b * L.ncell);
+    for (int k = 0; k < L.nk; ++k)
+      for (int j = 0; j < L.nj; ++j)
+        for (int i = 0; i < L.ni; ++i) {
+          const bool in = i >= L.lo[0] && i <= L.hi[0] && j >= L.lo[1] && j <= L.hi[1] && k >= L.lo[2] && k <= L.hi[2];
+          const int o = L.idx(k, j, i);
+          if (!in && !mask_out[(size_t)base + o]) zones_out[n++] = base + (unsigned)o;
+        }
   }
+  *nzones_out = n;
   return PB_OK;
 }

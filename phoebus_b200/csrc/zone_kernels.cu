@@ -388,10 +388,22 @@ struct C2PWork {
   const int *blocks; // block list or NULL (= all blocks of the pack)
   int nlist;         // blocks covered
   int shell;         // 1: ghost shell instead of the box
-  const unsigned *zones; // ghost plan: explicit zone ids (block * ncell + cell), nzones of them; overrides the rest
-  long long nzones;
+  const unsigned *zones; // ghost plan: the box of the nlist blocks (enumerated arithmetically: no dependent load in front of
+  long long nzones;      // the zone's own loads), followed by nzones explicit zone ids (block * ncell + cell)
 };
 PB_DEV bool c2p_zone_of_list(const C2PWork &w, const Lay &L, long long t, int &b, int &k, int &j, int &i) {
+  const long long nreg = w.reg.n(), dense = nreg * w.nlist;
+  if (t < dense) {
+    const int q = (int)(t / nreg);
+    b = w.blocks ? w.blocks[q] : q;
+    int rem = (int)(t - (long long)q * nreg);
+    i = w.reg.i0 + rem % w.reg.ni();
+    rem /= w.reg.ni();
+    j = w.reg.j0 + rem % w.reg.nj();
+    k = w.reg.k0 + rem / w.reg.nj();
+    return true;
+  }
+  t -= dense;
   if (t >= w.nzones) return false;
   const unsigned z = __ldg(w.zones + t);
   b = (int)(z / (unsigned)L.ncell);
@@ -1517,13 +1529,16 @@ int launch_c2p(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const i
   const C2PWork work{reg, nullptr, pack->nblocks, 0, nullptr, 0};
   return launch_c2p_work(pack, cfg, cons, work, reg.n() * pack->nblocks, zflags, s);
 }
-// c2p on the zones [from, to) of the pack's ghost plan (pack->c2p_zones)
-int launch_c2p_zones(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, long long from, long long to,
-                     unsigned char *zflags, cudaStream_t s) {
-  if (to <= from) return PB_OK;
+// ghost plan: c2p on the interior zones of a list of blocks (NULL: all blocks) and, with_ghosts, on the ghost zones the plan lists
+int launch_c2p_plan(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, bool with_ghosts,
+                    unsigned char *zflags, cudaStream_t s) {
   const Lay L(*cfg);
-  const C2PWork work{entire(L), nullptr, pack->nblocks, 0, pack->c2p_zones + from, to - from};
-  return launch_c2p_work(pack, cfg, cons, work, to - from, zflags, s);
+  const Region reg = interior(L);
+  const long long nz = with_ghosts ? pack->n_c2p_zones : 0;
+  const long long nthr = reg.n() * nlist + nz;
+  if (nthr <= 0) return PB_OK;
+  const C2PWork work{reg, blocks, nlist, 0, pack->c2p_zones, nz};
+  return launch_c2p_work(pack, cfg, cons, work, nthr, zflags, s);
 }
 // c2p on a list of blocks: which = 0 interior zones, 1 ghost shell, 2 entire block
 int launch_c2p_list(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, int which,

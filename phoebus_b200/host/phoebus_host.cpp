@@ -738,22 +738,23 @@ void Mesh::Allocate() {
   // ghost plan: ghost zones whose con2prim result is copied from the same-GPU neighbour (include/phoebus_b200.h)
   pack_.ghost_mask = nullptr;
   pack_.c2p_zones = nullptr;
-  for (int n = 0; n < 4; ++n) pack_.c2p_seg[n] = 0;
+  pack_.n_c2p_zones = 0;
   if (cfg.bc_prim) {
     std::vector<unsigned char> mask((size_t)nblocks * cells);
     std::vector<unsigned> zones((size_t)nblocks * cells);
-    long long seg[4];
-    CheckPb(pb_ghost_plan_host(&cfg, blocks_host.data(), nblocks, geom_host_.data(), floor_host_.data(),
-                               inner.empty() ? nullptr : inner.data(), (int)inner.size(), mask.data(), zones.data(), seg),
+    long long nz = 0;
+    CheckPb(pb_ghost_plan_host(&cfg, blocks_host.data(), nblocks, geom_host_.data(), floor_host_.data(), mask.data(), zones.data(), &nz),
             "pb_ghost_plan_host");
-    if (seg[3] < (long long)nblocks * cells) {
+    bool any = false;
+    for (unsigned char m : mask) any = any || m;
+    if (any) {
       unsigned char *mask_dev = (unsigned char *)dev(mask.size());
       CheckCuda(cudaMemcpy(mask_dev, mask.data(), mask.size(), cudaMemcpyHostToDevice), "ghost mask H2D");
-      unsigned *zones_dev = (unsigned *)dev(sizeof(unsigned) * (size_t)seg[3]);
-      CheckCuda(cudaMemcpy(zones_dev, zones.data(), sizeof(unsigned) * (size_t)seg[3], cudaMemcpyHostToDevice), "c2p zone list H2D");
+      unsigned *zones_dev = (unsigned *)dev(sizeof(unsigned) * (size_t)std::max<long long>(1, nz));
+      if (nz) CheckCuda(cudaMemcpy(zones_dev, zones.data(), sizeof(unsigned) * (size_t)nz, cudaMemcpyHostToDevice), "c2p zone list H2D");
       pack_.ghost_mask = mask_dev;
       pack_.c2p_zones = zones_dev;
-      for (int n = 0; n < 4; ++n) pack_.c2p_seg[n] = seg[n];
+      pack_.n_c2p_zones = nz;
     }
   }
   AddContainer("base");

@@ -290,44 +290,42 @@ class MeshPack:
         pk.n_bc_blocks = self.n_bc_blocks
         pk.inner_blocks = self.inner_blocks.data_ptr()
         pk.n_inner_blocks = self.n_inner_blocks
-        self._ghost_plan(pk, inner)
+        self._ghost_plan(pk)
         self.pack = pk
         self.flags_valid = False
 
-    def ghost_plan_host(self, inner=None):
-        """(mask [nblocks*ncell] u8, zones u32, seg[4]) of pb_ghost_plan_host for this pack — host arrays only"""
+    def ghost_plan_host(self):
+        """(mask [nblocks*ncell] u8, ids of the ghost zones that keep their own con2prim u32) of pb_ghost_plan_host for
+        this pack — host arrays only"""
         L = _lib.lib()
-        if inner is None:
-            inner = [n for n in range(self.nblocks) if not any(self.blocks_host[n].bc[f] != 0 for f in range(2 * self.ndim))]
+        nint = self.nx[0] * (self.nx[1] if self.ndim >= 2 else 1) * (self.nx[2] if self.ndim >= 3 else 1)
         mask = np.zeros(self.nblocks * self.ncell, dtype=np.uint8)
-        zones = np.zeros(self.nblocks * self.ncell, dtype=np.uint32)
-        seg = (C.c_longlong * 4)()
-        inn = np.ascontiguousarray(inner, dtype=np.int32)
+        zones = np.zeros(max(1, self.nblocks * (self.ncell - nint)), dtype=np.uint32)
+        n = C.c_longlong(0)
         cfg = self.p.make_cfg(self.gshape)
         _lib.check(L.pb_ghost_plan_host(C.byref(cfg), C.addressof(self.blocks_host), self.nblocks, self.geom_host.ctypes.data,
-                                        self.floor_host.ctypes.data, inn.ctypes.data if len(inner) else None, len(inner),
-                                        mask.ctypes.data, zones.ctypes.data, seg), "pb_ghost_plan_host")
-        return mask, zones[:seg[3]].copy(), tuple(seg)
+                                        self.floor_host.ctypes.data, mask.ctypes.data, zones.ctypes.data, C.byref(n)),
+                   "pb_ghost_plan_host")
+        return mask, zones[:n.value].copy()
 
-    def _ghost_plan(self, pk, inner):
+    def _ghost_plan(self, pk):
         """which ghost zones take their con2prim result from the same-GPU neighbour instead of solving again
         (pb_ghost_plan_host, csrc/ghost_plan_host.cpp); use_ghost_plan=False leaves the pack without a plan"""
         t = self.torch
         self.ghost_mask = self.c2p_zones = None
-        self.c2p_seg, self.n_deferred = (0, 0, 0, 0), 0
+        self.n_deferred, self.n_c2p_zones = 0, self.nblocks * self.ncell
         if not self.use_ghost_plan or not self.p.bc_prim:
             return
-        mask, zones, seg = self.ghost_plan_host(inner)
-        self.c2p_seg = seg
+        mask, zones = self.ghost_plan_host()
         self.n_deferred = int(mask.sum())
         if self.n_deferred == 0:
             return
+        self.n_c2p_zones = self.zones() + len(zones)  # interiors + the listed ghost zones
         self.ghost_mask = t.from_numpy(mask).to(self.device)
-        self.c2p_zones = t.from_numpy(zones).to(self.device)
+        self.c2p_zones = t.from_numpy(zones if len(zones) else np.zeros(1, dtype=np.uint32)).to(self.device)
         pk.ghost_mask = self.ghost_mask.data_ptr()
         pk.c2p_zones = self.c2p_zones.data_ptr()
-        for n in range(4):
-            pk.c2p_seg[n] = seg[n]
+        pk.n_c2p_zones = len(zones)
 
     def zones(self):
         """interior zones owned by this pack"""

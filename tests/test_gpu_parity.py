@@ -696,7 +696,7 @@ def test_con2prim_variants_bit_identical_and_statistics(name):
             out[mode] = {k: _np(getattr(mesh, k)).copy() for k in FIELDS}
             out[mode]["cons"] = _np(mesh.cons["base"]).copy()
             # with the ghost plan only the plan's zone list is solved (the deferred ghost zones copy the neighbour's result)
-            nstage, ncells = len(stage_tags(g)), (mesh.c2p_seg[3] if mesh.ghost_mask is not None else mesh.nblocks * mesh.ncell)
+            nstage, ncells = len(stage_tags(g)), mesh.n_c2p_zones
     finally:
         L.pb_set_option(b"c2p_arith", 2)
     for mode in (2, 0):
@@ -829,8 +829,7 @@ def test_ghost_plan_on_a_mesh_with_inner_blocks_changes_no_bit(force_split):
     ref, mref = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=False)
     out, mesh = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=True, force_split=force_split)
     assert mref.ghost_mask is None and mesh.ghost_mask is not None
-    seg = mesh.c2p_seg
-    assert 0 < seg[1] < seg[2] < seg[3] < mesh.nblocks * mesh.ncell
+    assert mesh.zones() < mesh.n_c2p_zones < mesh.nblocks * mesh.ncell and mesh.n_inner_blocks == 8
     assert mesh.n_deferred > 0.2 * mesh.nblocks * mesh.ncell
     for k in ref:
         assert np.array_equal(out[k], ref[k], equal_nan=True), k
