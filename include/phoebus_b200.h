@@ -127,6 +127,13 @@ typedef struct pb_pack {
   long long n_c2p_zones;
 } pb_pack_t;
 
+/* Per-MeshBlock allocations <-> the slabs of pb_pack_t. Parthenon allocates every variable per MeshBlock and variable
+ * (ref: external/parthenon/src/interface/variable.cpp); a host that cannot allocate them from one arena per field gathers
+ * them into the slab ([b][words_per_block], words_per_block = components * cells) before a cycle and scatters them back
+ * after it. block_ptrs_dev: DEVICE array of nblocks device pointers; at most 65535 blocks per call. */
+int pb_blocks_gather(double *slab, const double *const *block_ptrs_dev, int nblocks, long long words_per_block, void *stream);
+int pb_blocks_scatter(const double *slab, double *const *block_ptrs_dev, int nblocks, long long words_per_block, void *stream);
+
 /* Host-side construction of the ghost plan (ghost_plan_host.cpp states the conditions). blocks / geom_host / floor_host
  * are the HOST copies of what the pack holds on the device. mask_out: nblocks * cells bytes; zones_out: room for nblocks *
  * (cells - interior cells) entries, *nzones_out of them written. The caller uploads both. Returns PB_OK; a configuration the

@@ -86,6 +86,8 @@ SYMBOLS = {
     "pb_halo_exchange_local_ex": (C.c_int, [_PACK, _CFG, _P, C.c_int, _P]),
     "pb_ghost_plan_host": (C.c_int, [_CFG, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_longlong)]),
     "pb_ghost_plan_active": (C.c_int, [_PACK, _CFG]),
+    "pb_blocks_gather": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P]),
+    "pb_blocks_scatter": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P]),
     "pb_halo_nvar": (C.c_int, [_CFG]),
     "pb_halo_pack": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P, _P]),
     "pb_halo_unpack": (C.c_int, [_PACK, _CFG, _P, _P, C.c_int, _P, _P]),

@@ -708,6 +708,53 @@ extern "C" int pb_calculate_divb(const pb_pack_t *pack, const pb_cfg_t *cfg, con
   return check_launch("divb_kernel");
 }
 
+// ------------------------------------------------------------------ per-MeshBlock allocations <-> slabs
+// Parthenon allocates every variable per MeshBlock (ref: external/parthenon/src/interface/variable.cpp, one ParArray per
+// block and variable); pb_pack_t takes one slab per field. A host that cannot place its variables in such slabs gathers them
+// before a cycle and scatters them after it. gridDim.y = block, grid-stride over the block's words, 16-byte accesses when
+// both sides are aligned.
+namespace pb {
+template <bool GATHER>
+__global__ void block_copy_kernel(double *slab, double *const *block_ptrs, const long long words) {
+  const int b = blockIdx.y;
+  double *blk = block_ptrs[b];
+  double *sl = slab + (size_t)b * words;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((reinterpret_cast<size_t>(blk) | reinterpret_cast<size_t>(sl)) & 15) == 0) {
+    const long long n2 = words / 2;
+    double2 *a = reinterpret_cast<double2 *>(GATHER ? sl : blk);
+    const double2 *c = reinterpret_cast<const double2 *>(GATHER ? blk : sl);
+    for (long long q = t; q < n2; q += stride) a[q] = c[q];
+    if ((words & 1) && t == 0) (GATHER ? sl : blk)[words - 1] = (GATHER ? blk : sl)[words - 1];
+  } else {
+    for (long long q = t; q < words; q += stride) (GATHER ? sl : blk)[q] = (GATHER ? blk : sl)[q];
+  }
+}
+static int launch_block_copy(bool gather, double *slab, double *const *block_ptrs, int nblocks, long long words, cudaStream_t s) {
+  if (!slab || !block_ptrs) return set_error(PB_EINVAL, "pb_blocks_gather / scatter: NULL argument");
+  if (nblocks <= 0 || words <= 0) return PB_OK;
+  if (nblocks > 65535) return set_error(PB_EINVAL, "pb_blocks_gather / scatter: more than 65535 blocks per call");
+  long long gx = (words / 2 + 255) / 256;
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  const dim3 grid((unsigned)gx, (unsigned)nblocks);
+  if (gather) block_copy_kernel<true><<<grid, 256, 0, s>>>(slab, block_ptrs, words);
+  else block_copy_kernel<false><<<grid, 256, 0, s>>>(slab, block_ptrs, words);
+  return check_launch("block_copy_kernel");
+}
+} // namespace pb
+
+extern "C" int pb_blocks_gather(double *slab, const double *const *block_ptrs_dev, int nblocks, long long words_per_block,
+                                void *stream) {
+  return launch_block_copy(true, slab, const_cast<double *const *>(reinterpret_cast<const double *const *>(block_ptrs_dev)), nblocks,
+                           words_per_block, (cudaStream_t)stream);
+}
+extern "C" int pb_blocks_scatter(const double *slab, double *const *block_ptrs_dev, int nblocks, long long words_per_block,
+                                 void *stream) {
+  return launch_block_copy(false, const_cast<double *>(slab), block_ptrs_dev, nblocks, words_per_block, (cudaStream_t)stream);
+}
+
 extern "C" int pb_weighted_sum(const double *x, const double *y, double w1, double w2, double *z, long long n,
                                void *stream) {
   if (n <= 0) return PB_OK;

@@ -833,3 +833,30 @@ def test_ghost_plan_on_a_mesh_with_inner_blocks_changes_no_bit(force_split):
     assert mesh.n_deferred > 0.2 * mesh.nblocks * mesh.ncell
     for k in ref:
         assert np.array_equal(out[k], ref[k], equal_nan=True), k
+
+
+def test_per_block_allocations_gather_scatter_round_trip():
+    """pb_blocks_gather / pb_blocks_scatter: per-MeshBlock allocations (as Parthenon makes them) <-> the slab layout of pb_pack_t,
+    aligned and misaligned block pointers, odd word counts"""
+    import torch
+    from phoebus_b200 import _lib
+    L = _lib.lib()
+    dev = _dev()
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    for words, off in ((10 * 40 ** 3, 0), (1001, 0), (1001, 1), (64, 1)):
+        nb = 7
+        store = [torch.rand(words + 2, dtype=torch.float64, generator=gen).to(dev) for _ in range(nb)]
+        blocks = [t[off:off + words] for t in store]
+        ptrs = torch.tensor([b.data_ptr() for b in blocks], dtype=torch.int64, device=dev)
+        slab = torch.zeros(nb, words, dtype=torch.float64, device=dev)
+        _lib.check(L.pb_blocks_gather(slab.data_ptr(), ptrs.data_ptr(), nb, words, None), "pb_blocks_gather")
+        torch.cuda.synchronize()
+        assert all(torch.equal(slab[n], blocks[n]) for n in range(nb))
+        slab.mul_(2.0)
+        keep = [t.clone() for t in store]
+        _lib.check(L.pb_blocks_scatter(slab.data_ptr(), ptrs.data_ptr(), nb, words, None), "pb_blocks_scatter")
+        torch.cuda.synchronize()
+        for n in range(nb):
+            assert torch.equal(blocks[n], slab[n])
+            # words outside the block's extent stay untouched
+            assert torch.equal(store[n][:off], keep[n][:off]) and torch.equal(store[n][off + words:], keep[n][off + words:])
