@@ -85,6 +85,8 @@ extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks,
           const int nb = blk.nbr[(off[0] + 1) + 3 * (off[1] + 1) + 9 * (off[2] + 1)];
           if (nb < 0 || nb >= nblocks) continue;
           const pb_block_t &src = blocks[nb];
+          // the neighbour must name this block at the opposite offset (the push form of the copy starts from the source)
+          if (src.nbr[(-off[0] + 1) + 3 * (-off[1] + 1) + 9 * (-off[2] + 1)] != b) continue;
           const int si = i - off[0] * nx[0], sj = j - off[1] * nx[1], sk = k - off[2] * nx[2];
           // tables
           const size_t g0 = gcell_of(k, j, i), g1 = gcell_of(sk, sj, si);
