@@ -860,3 +860,69 @@ def test_per_block_allocations_gather_scatter_round_trip():
             assert torch.equal(blocks[n], slab[n])
             # words outside the block's extent stay untouched
             assert torch.equal(store[n][:off], keep[n][:off]) and torch.equal(store[n][off + words:], keep[n][off + words:])
+
+
+def test_benchmark_size_properties_256cube():
+    """BASELINE.json configs[4] at its full single-GPU size (256^3 zones, 512 MeshBlocks of 32^3, FM torus), through
+    size-independent properties: (i) the ghost plan changes no bit of any field of any zone (device-side checksums of the
+    bit patterns, independent reductions per field) nor the floor counters; (ii) flux-CT preserves div B: it is not zero
+    after the reference's start-up sequence (the beta normalisation rescales B on the interiors only, torus.cpp:525-737,
+    and post-initialisation communication is off by default), but two cycles change it by round-off of |B| / dx only, in
+    every zone whose divergence stencil lies inside one MeshBlock; (iii) every field stays finite; (iv) the total baryon number changes only by what the
+    outflow boundaries and floors can account for (< 1e-6 relative in two cycles at this dt)."""
+    import torch
+    from phoebus_b200 import _lib
+    from phoebus_b200.driver import FluidDriver
+    from phoebus_b200.mesh import MeshPack
+    from phoebus_b200.params import FluidParams, ParameterInput
+    from phoebus_b200.pgen import init_torus, torus_problem_modifier
+    L = _lib.lib()
+
+    def run(use_ghost_plan):
+        ov = ["parthenon/mesh/nx%d=256" % (d + 1) for d in range(3)] + ["parthenon/meshblock/nx%d=32" % (d + 1) for d in range(3)]
+        ov += ["parthenon/time/dt_init_fact=1e-2"]
+        pin = ParameterInput(open(os.path.join(ROOT_DIR, "phoebus_b200", "decks", "torus3d.pin")).read(), ov)
+        torus_problem_modifier(pin)
+        mesh = MeshPack(FluidParams(pin), device=_dev(), use_ghost_plan=use_ghost_plan)
+        drv = FluidDriver(mesh)
+        init_torus(mesh, drv)
+        drv.ensure_flags()
+        mesh.counters.zero_()
+        h0 = drv.history()
+        ng = mesh.ng
+        core = (slice(None),) + (slice(ng + 1, -ng - 1),) * 3
+
+        def divb_now():
+            d = torch.zeros((mesh.nblocks,) + mesh.shape, dtype=torch.float64, device=_dev())
+            _lib.check(L.pb_calculate_divb(C.byref(mesh.pack), C.byref(mesh.cfg), mesh.cons["base"].data_ptr(), d.data_ptr(), None), "divb")
+            return d[core].clone()
+
+        d0 = divb_now()
+        dt = 1e-2 * drv.estimate_dt()
+        for _ in range(2):
+            drv.step(dt)
+        torch.cuda.synchronize()
+        sums = {}
+        for k in FIELDS + ("cons",):
+            t = mesh.cons["base"] if k == "cons" else getattr(mesh, k)
+            v = t.reshape(-1).view(torch.int64)
+            assert bool(torch.isfinite(t).all()), k
+            sums[k] = (int(v.sum()), int((v >> 11).bitwise_xor(v).sum()), int(v[::7].sum()))
+        sums["counters"] = tuple(int(x) for x in mesh.counters.cpu())
+        inner = (divb_now() - d0).abs().max().item()
+        bmax = mesh.cons["base"][:, 5:8].abs().max().item()
+        h1 = drv.history()
+        planned = mesh.ghost_mask is not None
+        dxmin = float(mesh.bdx.min())
+        del d0, drv, mesh
+        torch.cuda.empty_cache()
+        return sums, inner, bmax, h0, h1, planned, dxmin
+
+    a = run(True)
+    b = run(False)
+    assert a[5] and not b[5]
+    assert a[0] == b[0], {k: (a[0][k], b[0][k]) for k in a[0] if a[0][k] != b[0][k]}
+    for sums, divb, bmax, h0, h1, _, dxmin in (a, b):
+        assert bmax > 0 and divb <= 1e-11 * bmax / dxmin, (divb, bmax, dxmin)
+        m0, m1 = h0["total baryon number"], h1["total baryon number"]
+        assert abs(m1 - m0) <= 1e-6 * abs(m0), (m0, m1)
