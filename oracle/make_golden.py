@@ -69,6 +69,14 @@ CASES.update({
                        + ["phoebus/%sx%d_bc=reflect" % (io, d) for d in (1, 2) for io in "io"], 2, 0,
                        {"REF_DUMP_PERTURB": "0.2"}),
 })
+# the reference's DEFAULT ghost depth for linear reconstruction (nghost = 2): the stencil loads of the flux kernels must
+# stay inside the slab (round-1 review), periodic halos and a reflecting shock tube at two ghost zones
+CASES.update({
+    "linmodes2d_ng2": ("mink", "linear_modes_3d", ["hydro_modes/physics=mhd", "hydro_modes/mode=fast", "parthenon/mesh/nghost=2"]
+                       + B3(16, 16, 1, 8, 8, 1), 2, 0, {"REF_DUMP_PERTURB": "0.2"}),
+    "shocktube_ng2": ("mink", "mhd_shocktube", ["parthenon/mesh/nx1=64", "parthenon/mesh/nghost=2", "fluid/recon=linear",
+                                                "parthenon/time/dt_init_fact=1.0"], 2, 0),
+})
 # the production block shape: 3-D FMKS torus with 32^3 MeshBlocks (2x2x2 of them), stored as per-array hashes
 # (REF_DUMP_FIELDS=hash); the test rebuilds the initial state with the product's own torus pgen + the same perturbation
 HASHED = {

@@ -7,7 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 CASES = ["shocktube", "linmodes2d", "blast3d", "torus2d",
          # round 2: 3-D FMKS (the benchmarked configuration), real c2p failures, polar / reflect / conserved-FMKS boundaries
-         "torus3d", "torus2d_fail", "torus2d_polar", "torus2d_cons", "reflect3d", "reflect2d_prim"]
+         "torus3d", "torus2d_fail", "torus2d_polar", "torus2d_cons", "reflect3d", "reflect2d_prim",
+         # the reference's default ghost depth for linear reconstruction (nghost = 2): stencil loads stay inside the slab
+         "linmodes2d_ng2", "shocktube_ng2"]
 
 
 def load_case(name):

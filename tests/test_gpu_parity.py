@@ -736,7 +736,7 @@ def test_cuda_graph_replay_matches_reference_dumps(name):
 
 
 @pytest.mark.parametrize("tma", [1, 0])
-@pytest.mark.parametrize("name", ["shocktube", "linmodes2d", "blast3d", "torus3d", "torus2d"])
+@pytest.mark.parametrize("name", ["shocktube", "linmodes2d", "blast3d", "torus3d", "torus2d", "linmodes2d_ng2", "shocktube_ng2"])
 def test_fused_flux_kernel_tma_and_cpasync_match_oracle(name, tma):
     """the fused reconstruction + Riemann kernel (no ql / qr in HBM) with its stencil tile staged by ONE TMA tensor load per
     CTA (cp.async.bulk.tensor.5d + mbarrier) or by per-thread cp.async copies: fluxes and face speeds of the oracle, 1-D to 3-D"""
