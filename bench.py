@@ -315,7 +315,8 @@ def run_ours(args):
                    "halo_transport": ("ncclSend/ncclRecv inside the C ABI" if args.halo == "nccl" else "torch.distributed") if world > 1 else None,
                    "cuda_graphs": bool(args.graphs),
                    # ghost zones whose con2prim result is copied from the same-GPU neighbour (identical inputs and tables)
-                   "ghost_plan": {"deferred_zones": int(getattr(mesh, "n_deferred", 0)), "con2prim_zones": int(mesh.n_c2p_zones),
+                   "ghost_plan": {"deferred_zones": int(getattr(mesh, "n_deferred", 0)), "twin_zones": int(getattr(mesh, "n_twin", 0)),
+                                  "con2prim_zones": int(mesh.n_c2p_zones),
                                   "all_zones": int(mesh.nblocks * mesh.ncell)} if mesh.ghost_mask is not None else None,
                    "l2": "working set %.1f GB per GPU >> 126 MB L2" % (mesh.bytes_allocated() / 1e9)},
         "roofline": {"bound": "hbm", "kernel": kname, "co_bound": "fp64 pipe (no FMA contraction: bit parity with the reference)",

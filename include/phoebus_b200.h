@@ -122,9 +122,17 @@ typedef struct pb_pack {
    * zones and on the ghost zones listed in c2p_zones, and fills the ghost zones flagged in ghost_mask from the interior
    * zone of their same-pack neighbour AFTER con2prim: the reference solves those zones twice with identical inputs and
    * tables (ghost_plan_host.cpp). The task-level entry points (pb_cons_to_prim, pb_halo_exchange_local, ...) ignore it. */
-  const unsigned char *ghost_mask; /* device [b][cells]: 1 = deferred ghost zone */
+  const unsigned char *ghost_mask; /* device [b][cells]: 1 = deferred ghost zone, 2 = twin (below) */
   const unsigned *c2p_zones;       /* device [n_c2p_zones]: ids b * cells + cell of the ghost zones that are solved */
   long long n_c2p_zones;
+  /* twins (optional part of the plan): x1 ghost zones that would be deferred but for tables that differ from the
+   * neighbour's in the last place. Their con2prim runs on the neighbour's inputs with this block's tables into twin_buf
+   * (launched with the pre-con2prim ghost copy, before any con2prim of the stage overwrites those inputs) and the deferred
+   * copy takes them from there. */
+  const unsigned *twin_zones;      /* device [n_twin]: zone ids, ordered (block, x1 ghost column, k, j) */
+  long long n_twin;
+  double *twin_buf;                /* device [ncons + nprim + 3 + ndim][S], S = pb_twin_entries(cfg, nblocks) */
+  unsigned char *twin_flags;       /* device [S] */
 } pb_pack_t;
 
 /* Per-MeshBlock allocations <-> the slabs of pb_pack_t. Parthenon allocates every variable per MeshBlock and variable
@@ -136,10 +144,14 @@ int pb_blocks_scatter(const double *slab, double *const *block_ptrs_dev, int nbl
 
 /* Host-side construction of the ghost plan (ghost_plan_host.cpp states the conditions). blocks / geom_host / floor_host
  * are the HOST copies of what the pack holds on the device. mask_out: nblocks * cells bytes; zones_out: room for nblocks *
- * (cells - interior cells) entries, *nzones_out of them written. The caller uploads both. Returns PB_OK; a configuration the
+ * (cells - interior cells) entries, *nzones_out of them written; twins_out (optional, NULL: no twins — those zones are
+ * listed in zones_out instead): room for nblocks * 2 ng * nk * nj entries. The caller uploads the arrays. Returns PB_OK; a configuration the
  * shortcut does not apply to (bc_vars = conserved, floor type RRhoSie) yields an all-zero mask and every ghost zone listed. */
 int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks, int nblocks, const double *geom_host,
-                       const double *floor_host, unsigned char *mask_out, unsigned *zones_out, long long *nzones_out);
+                       const double *floor_host, unsigned char *mask_out, unsigned *zones_out, long long *nzones_out,
+                       unsigned *twins_out, long long *ntwins_out);
+/* entries of the twin side buffer: nblocks * 2 ng * nk * nj (every x1 ghost column of every block has a slot) */
+long long pb_twin_entries(const pb_cfg_t *cfg, int nblocks);
 /* Same-GPU ghost copy with the plan: phase 0 = every ghost zone (pb_halo_exchange_local); 1 = all but the deferred zones;
  * 2 = only the deferred zones, every field con2prim reads or writes (conserved, primitives, temperature, c2p_mu, fail,
  * cell signal speeds, zone flags), to be called after con2prim and before the fixup. */

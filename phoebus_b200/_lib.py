@@ -54,7 +54,8 @@ class PbPack(C.Structure):
                 ("csig", C.c_void_p), ("fsig", C.c_void_p), ("flux", C.c_void_p), ("emf", C.c_void_p),
                 ("zflags", C.c_void_p), ("bc_blocks", C.c_void_p), ("n_bc_blocks", C.c_int), ("gsrc", C.c_void_p),
                 ("inner_blocks", C.c_void_p), ("n_inner_blocks", C.c_int), ("recon_lr", C.c_void_p),
-                ("ghost_mask", C.c_void_p), ("c2p_zones", C.c_void_p), ("n_c2p_zones", C.c_longlong)]
+                ("ghost_mask", C.c_void_p), ("c2p_zones", C.c_void_p), ("n_c2p_zones", C.c_longlong),
+                ("twin_zones", C.c_void_p), ("n_twin", C.c_longlong), ("twin_buf", C.c_void_p), ("twin_flags", C.c_void_p)]
 
 
 # every symbol include/phoebus_b200.h declares: name -> (restype, argtypes)
@@ -84,7 +85,8 @@ SYMBOLS = {
     "pb_prim_to_cons": (C.c_int, [_PACK, _CFG, _P, _I2, _I2, _I2, _P]),
     "pb_halo_exchange_local": (C.c_int, [_PACK, _CFG, _P, _P]),
     "pb_halo_exchange_local_ex": (C.c_int, [_PACK, _CFG, _P, C.c_int, _P]),
-    "pb_ghost_plan_host": (C.c_int, [_CFG, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_longlong)]),
+    "pb_ghost_plan_host": (C.c_int, [_CFG, _P, C.c_int, _P, _P, _P, _P, C.POINTER(C.c_longlong), _P, C.POINTER(C.c_longlong)]),
+    "pb_twin_entries": (C.c_longlong, [_CFG, C.c_int]),
     "pb_ghost_plan_active": (C.c_int, [_PACK, _CFG]),
     "pb_blocks_gather": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P]),
     "pb_blocks_scatter": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P]),

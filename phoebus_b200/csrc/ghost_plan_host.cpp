@@ -46,9 +46,15 @@ struct HostLay {
 inline bool same_bits(double a, double b) { return std::memcmp(&a, &b, sizeof(double)) == 0; }
 } // namespace
 
+extern "C" long long pb_twin_entries(const pb_cfg_t *cfg, int nblocks) {
+  if (!cfg || nblocks <= 0) return 0;
+  const HostLay L(*cfg);
+  return (long long)nblocks * 2 * L.ng * L.nk * L.nj;
+}
+
 extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks, int nblocks, const double *geom_host,
                                   const double *floor_host, unsigned char *mask_out, unsigned *zones_out,
-                                  long long *nzones_out) {
+                                  long long *nzones_out, unsigned *twins_out, long long *ntwins_out) {
   if (!cfg || !blocks || nblocks <= 0 || !geom_host || !floor_host || !mask_out || !zones_out || !nzones_out) return PB_EINVAL;
   const HostLay L(*cfg);
   if ((long long)nblocks * L.ncell >= (1ll << 32)) return PB_EINVAL;
@@ -59,6 +65,9 @@ extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks,
   };
   std::memset(mask_out, 0, (size_t)nblocks * L.ncell);
   const bool possible = cfg->bc_prim && cfg->floor_type != 4;
+  // twin entries live in a side buffer of nblocks * 2 ng * nk * nj entries addressed with 32-bit strides
+  const bool twins = twins_out && ntwins_out && (long long)nblocks * 2 * L.ng * L.nk * L.nj < (1ll << 31);
+  if (ntwins_out) *ntwins_out = 0;
   const int nx[3] = {cfg->nx[0], cfg->nx[1], cfg->nx[2]};
 #pragma omp parallel for schedule(static)
   for (int b = 0; b < nblocks; ++b) {
@@ -100,8 +109,26 @@ extern "C" int pb_ghost_plan_host(const pb_cfg_t *cfg, const pb_block_t *blocks,
             const double *f1 = floor_host + (size_t)src.floor_slot * 4 * L.ni;
             ok = same_bits(f0[i], f1[si]) && same_bits(f0[L.ni + i], f1[L.ni + si]);
           }
+          // 1: the neighbour's result is the ghost zone's result. 2 ("twin"): same inputs, but this block's tables differ
+          // from the neighbour's in the last place (x1 ghost columns: block coordinates are xmin_block + (i + 1/2) dx_block)
+          // — solved from the neighbour's inputs with THIS block's tables in a side buffer (zone_kernels.cu: twin kernels),
+          // so that neither a sparse pre-con2prim copy nor 8-byte holes in the deferred copy remain
           if (ok) mask_out[(size_t)b * L.ncell + L.idx(k, j, i)] = 1;
+          else if (twins && off[0] != 0) mask_out[(size_t)b * L.ncell + L.idx(k, j, i)] = 2;
         }
+  }
+  if (twins) { // ordered (block, x1 ghost column, k, j): consecutive entries are consecutive in the side buffer
+    long long m = 0;
+    for (int b = 0; b < nblocks; ++b)
+      for (int c = 0; c < 2 * L.ng; ++c) {
+        const int i = c < L.ng ? c : c + nx[0];
+        for (int k = 0; k < L.nk; ++k)
+          for (int j = 0; j < L.nj; ++j) {
+            const size_t z = (size_t)b * L.ncell + L.idx(k, j, i);
+            if (mask_out[z] == 2) twins_out[m++] = (unsigned)z;
+          }
+      }
+    *ntwins_out = m;
   }
   // the ghost zones that keep their own con2prim (interior zones are enumerated arithmetically by the kernels)
   long long n = 0;

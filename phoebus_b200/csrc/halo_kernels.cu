@@ -11,6 +11,7 @@
 #include "pb_host.hpp"
 
 namespace pb {
+int launch_twins(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, cudaStream_t s); // zone_kernels.cu
 
 struct HaloFields {
   Real *ptr[5];  // cons, prim, temp, c2p_mu, fail
@@ -82,6 +83,40 @@ PB_DEV void halo_copy_zone(const pb_pack_t &pack, const HaloFields &hf, const in
   }
 }
 
+// Phase 2 for a twin zone: every field from the side-buffer entry (twin_kernel, zone_kernels.cu) instead of the neighbour
+template <bool MHD>
+PB_DEV void halo_copy_twin(const pb_pack_t &pack, const HaloFields &hf, const pb_cfg_t &cfg, const Lay &L, const int b, const int k,
+                           const int j, const int i) {
+  constexpr int NCn = NC<MHD>::ncons, NP = NC<MHD>::nprim;
+  const TwinBuf tb(pack, L, cfg);
+  const int e = tb.entry(b, k, j, i);
+  const size_t S = (size_t)tb.S, N = (size_t)L.ncell, o = (size_t)L.idx(k, j, i);
+  const Real *src = tb.base + e;
+  Real v[NCn], q[NP], w[3], c[3];
+#pragma unroll
+  for (int n = 0; n < NCn; ++n) v[n] = src[n * S];
+#pragma unroll
+  for (int n = 0; n < NP; ++n) q[n] = src[(NCn + n) * S];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) w[f] = src[(NCn + NP + f) * S];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    if (d < L.ndim) c[d] = src[(NCn + NP + 3 + d) * S];
+  const unsigned char zf = tb.flags[e];
+  Real *cd = hf.ptr[0] + (size_t)b * NCn * N + o;
+#pragma unroll
+  for (int n = 0; n < NCn; ++n) cd[n * N] = v[n];
+  Real *pd = hf.ptr[1] + (size_t)b * NP * N + o;
+#pragma unroll
+  for (int n = 0; n < NP; ++n) pd[n * N] = q[n];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) hf.ptr[2 + f][(size_t)b * N + o] = w[f];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    if (d < L.ndim) pack.csig[((size_t)b * L.ndim + d) * N + o] = c[d];
+  if (pack.zflags) pack.zflags[(size_t)b * N + o] = zf;
+}
+
 // One thread per ghost zone (Shell enumeration: rows along x1 stay contiguous).
 // PHASE (ghost plan, ghost_plan_host.cpp): 0 every ghost zone; 1 skip the zones flagged in pack.ghost_mask; 2 only
 // those, after con2prim, with the cell signal speeds and the zone flags on top of the exchanged fields.
@@ -97,8 +132,12 @@ __global__ void __launch_bounds__(256) halo_local_kernel(const pb_pack_t pack, c
   sh.cell(L, (int)(t % sh.n), k, j, i);
   const int o = L.idx(k, j, i);
   if (PHASE != 0) {
-    const bool deferred = pack.ghost_mask[(size_t)b * N + o] != 0;
-    if (deferred != (PHASE == 2)) return;
+    const unsigned char m = pack.ghost_mask[(size_t)b * N + o];
+    if ((m != 0) != (PHASE == 2)) return;
+    if (PHASE == 2 && m == 2) { // twin: the zone's own con2prim result waits in the side buffer (zone_kernels.cu)
+      halo_copy_twin<MHD>(pack, hf, cfg, L, b, k, j, i);
+      return;
+    }
   }
   const int o1 = i < L.is ? -1 : (i > L.ie ? 1 : 0);
   const int o2 = j < L.js ? -1 : (j > L.je ? 1 : 0);
@@ -189,7 +228,12 @@ extern "C" int pb_halo_exchange_local_ex(const pb_pack_t *pack, const pb_cfg_t *
     else PB_HALO(false, false);
   }
 #undef PB_HALO
-  return check_launch("halo_local_kernel");
+  rc = check_launch("halo_local_kernel");
+  if (rc) return rc;
+  // the twins are solved with every pre-con2prim copy, from their neighbours' inputs before any con2prim overwrites them
+  // (phase 0 too: a full exchange may precede a planned post phase)
+  if (phase != 2 && pack->ghost_mask && cfg->bc_prim) return launch_twins(pack, cfg, cons, st);
+  return PB_OK;
 }
 
 extern "C" int pb_halo_exchange_local(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, void *stream) {

@@ -59,6 +59,16 @@ template <bool MHD> struct ZonePtr {
     fail = pack.fail + (size_t)b * L.ncell + o;
     csig = pack.csig + (size_t)b * L.ndim * L.ncell + o;
   }
+  // a zone whose fields live in the twin side buffer (entry e of S)
+  PB_DEV ZonePtr(const TwinBuf &tb, int e) : ncell(tb.S) {
+    const size_t S = (size_t)tb.S;
+    cons = tb.base + e;
+    prim = cons + NC<MHD>::ncons * S;
+    temp = prim + NC<MHD>::nprim * S;
+    mu = temp + S;
+    fail = mu + S;
+    csig = fail + S;
+  }
 };
 
 // c2p on one zone with the reference's write pattern: nothing is written when the NaN guard trips,
@@ -1388,6 +1398,76 @@ __global__ void dt_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Region
   }
 }
 
+// ------------------------------------------------------------------ twins of the ghost plan (ghost_plan_host.cpp)
+// An x1 ghost zone whose tables differ from the neighbour's in the last place is solved from the neighbour's INPUTS (what
+// the exchange would have put there: conserved state and c2p_mu; the previous primitives / temperature only on the paths
+// where the reference leaves them untouched) with its own tables, exactly as c2p_thread solves a zone, BEFORE any con2prim
+// of the stage overwrites those inputs: the kernel is launched with the pre-con2prim ghost copy. The result waits in the
+// side buffer; the deferred copy (halo_kernels.cu, phase 2) moves it into the ghost zone together with its row.
+PB_DEV void twin_decode(const Lay &L, unsigned z, int &b, int &k, int &j, int &i) {
+  b = (int)(z / (unsigned)L.ncell);
+  int rem = (int)(z - (unsigned)b * (unsigned)L.ncell);
+  i = rem % L.ni;
+  rem /= L.ni;
+  j = rem % L.nj;
+  k = rem / L.nj;
+}
+template <bool MHD>
+__global__ void __launch_bounds__(128, 4) twin_kernel(const pb_pack_t pack, const pb_cfg_t cfg, const Real *__restrict__ cons,
+                                                      unsigned long long *err_count) {
+  constexpr int NP = NC<MHD>::nprim, NCn = NC<MHD>::ncons;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= pack.n_twin) return;
+  const Lay L(cfg);
+  const size_t N = (size_t)L.ncell;
+  int b, k, j, i;
+  twin_decode(L, __ldg(pack.twin_zones + e), b, k, j, i);
+  const int o1 = i < L.is ? -1 : (i > L.ie ? 1 : 0);
+  const int o2 = j < L.js ? -1 : (j > L.je ? 1 : 0);
+  const int o3 = k < L.ks ? -1 : (k > L.ke ? 1 : 0);
+  const pb_block_t &blk = pack.blocks[b];
+  const size_t nb = (size_t)blk.nbr[(o1 + 1) + 3 * (o2 + 1) + 9 * (o3 + 1)];
+  const size_t so = (size_t)L.idx(k - o3 * cfg.nx[2], j - o2 * cfg.nx[1], i - o1 * cfg.nx[0]);
+  const GeomTab gt(cfg, pack.geom, blk.geom_slot);
+  PointGeom g;
+  g.load(gt, 0, gt.cell(k, j, i));
+  const FloorCtx fc = cell_floor_ctx(pack, blk, L, k, j, i);
+  const TwinBuf tb(pack, L, cfg);
+  const int en = tb.entry(b, k, j, i);
+  const ZonePtr<MHD> z(tb, en);
+  const size_t S = (size_t)tb.S;
+  Real U[NCn], P[NP];
+#pragma unroll
+  for (int n = 0; n < NCn; ++n) U[n] = cons[(nb * NCn + n) * N + so];
+  *z.mu = pack.c2p_mu[nb * N + so];
+#pragma unroll
+  for (int n = 0; n < NCn; ++n) z.cons[n * S] = U[n];
+  const bool nan_in = isnan(U[CRHO]) + isnan(U[CMOM]) + isnan(U[CENG]) > 0;
+  // a NaN with a private payload marks "the solve wrote nothing here" (NaN guard, unbracketed root)
+  const long long unwritten = 0x7ff8c2b0b2000001ll;
+  *z.temp = __longlong_as_double(unwritten);
+  const bool ok = c2p_zone_global<MHD, 1>(cfg, fc, g, z, L.ndim, U, P, err_count);
+  if (__double_as_longlong(*z.temp) == unwritten) {
+    // rare: the reference's ghost zone keeps the exchanged primitives and temperature and its own previous signal speeds
+    // (they are not exchanged); an unbracketed root has written the magnetic field components only
+#pragma unroll
+    for (int n = 0; n < NP; ++n) {
+      if (MHD && !nan_in && n >= PB_ && n < PB_ + 3) continue;
+      z.prim[n * S] = pack.prim[(nb * NP + n) * N + so];
+    }
+    *z.temp = pack.temp[nb * N + so];
+    const size_t o = (size_t)L.idx(k, j, i);
+    for (int d = 0; d < L.ndim; ++d) z.csig[d * S] = pack.csig[((size_t)b * L.ndim + d) * N + o];
+  }
+  *z.fail = ok ? 1.0 : 0.0;
+  unsigned char f = ok ? 0 : ZF_FAIL;
+  if (cfg.enable_floors) {
+    if (!ok) load_comps<NP>(z.prim, tb.S, P);
+    if (floors_needed<MHD>(cfg, fc, g, P)) f |= ZF_FLOOR;
+  }
+  tb.flags[en] = f;
+}
+
 static unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 static Region entire(const Lay &L) { return Region{0, L.ni - 1, 0, L.nj - 1, 0, L.nk - 1}; }
@@ -1539,6 +1619,16 @@ int launch_c2p_plan(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, co
   if (nthr <= 0) return PB_OK;
   const C2PWork work{reg, blocks, nlist, 0, pack->c2p_zones, nz};
   return launch_c2p_work(pack, cfg, cons, work, nthr, zflags, s);
+}
+// launched with the pre-con2prim ghost copy (halo_kernels.cu): the twins read their neighbours' inputs before any con2prim runs
+int launch_twins(const pb_pack_t *pack, const pb_cfg_t *cfg, const double *cons, cudaStream_t s) {
+  if (pack->n_twin <= 0 || !pack->twin_zones) return PB_OK;
+  if (!pack->twin_buf || !pack->twin_flags) return set_error(PB_EINVAL, "ghost plan: twin_zones without twin_buf / twin_flags");
+  PB_NEED("ghost plan twins", PB_F(pack, temp), PB_F(pack, c2p_mu), PB_F(pack, csig));
+  const unsigned grid = grid_for(pack->n_twin, 128);
+  if (cfg->mhd) twin_kernel<true><<<grid, 128, 0, s>>>(*pack, *cfg, cons, err_counter());
+  else twin_kernel<false><<<grid, 128, 0, s>>>(*pack, *cfg, cons, err_counter());
+  return check_launch("twin_kernel");
 }
 // c2p on a list of blocks: which = 0 interior zones, 1 ghost shell, 2 entire block
 int launch_c2p_list(const pb_pack_t *pack, const pb_cfg_t *cfg, double *cons, const int *blocks, int nlist, int which,

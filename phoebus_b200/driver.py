@@ -217,6 +217,8 @@ class FluidDriver:
         plan = bool(self.L.pb_ghost_plan_active(*self._pk()))
         if plan:
             n += 1  # the deferred ghost zones are copied after con2prim
+            if getattr(m, "n_twin", 0):
+                n += 1  # the twin solve, launched with the pre-con2prim ghost copy
         if self.dist is not None:
             n += 2  # one pack and one unpack launch for all peers
             if self.L.pb_early_c2p_pays(C.byref(m.pack)):

@@ -739,11 +739,18 @@ void Mesh::Allocate() {
   pack_.ghost_mask = nullptr;
   pack_.c2p_zones = nullptr;
   pack_.n_c2p_zones = 0;
+  pack_.twin_zones = nullptr;
+  pack_.n_twin = 0;
+  pack_.twin_buf = nullptr;
+  pack_.twin_flags = nullptr;
   if (cfg.bc_prim) {
     std::vector<unsigned char> mask((size_t)nblocks * cells);
     std::vector<unsigned> zones((size_t)nblocks * cells);
-    long long nz = 0;
-    CheckPb(pb_ghost_plan_host(&cfg, blocks_host.data(), nblocks, geom_host_.data(), floor_host_.data(), mask.data(), zones.data(), &nz),
+    const long long S = pb_twin_entries(&cfg, nblocks);
+    std::vector<unsigned> twins((size_t)std::max<long long>(1, S));
+    long long nz = 0, nt = 0;
+    CheckPb(pb_ghost_plan_host(&cfg, blocks_host.data(), nblocks, geom_host_.data(), floor_host_.data(), mask.data(), zones.data(), &nz,
+                               twins.data(), &nt),
             "pb_ghost_plan_host");
     bool any = false;
     for (unsigned char m : mask) any = any || m;
@@ -755,6 +762,14 @@ void Mesh::Allocate() {
       pack_.ghost_mask = mask_dev;
       pack_.c2p_zones = zones_dev;
       pack_.n_c2p_zones = nz;
+      if (nt) {
+        unsigned *tw_dev = (unsigned *)dev(sizeof(unsigned) * (size_t)nt);
+        CheckCuda(cudaMemcpy(tw_dev, twins.data(), sizeof(unsigned) * (size_t)nt, cudaMemcpyHostToDevice), "twin list H2D");
+        pack_.twin_zones = tw_dev;
+        pack_.n_twin = nt;
+        pack_.twin_buf = (double *)dev(sizeof(double) * (size_t)S * (size_t)(ncons + nprim + 3 + ndim));
+        pack_.twin_flags = (unsigned char *)dev((size_t)S);
+      }
     }
   }
   AddContainer("base");
@@ -824,6 +839,8 @@ std::shared_ptr<MeshBlockData<Real>> Mesh::GetBlockData(int b, const std::string
   p.n_inner_blocks = 0;
   p.ghost_mask = nullptr; // the plan describes the whole pack
   p.c2p_zones = nullptr;
+  p.twin_zones = nullptr;
+  p.n_twin = 0;
   rc->pack = p;
   rc->cons = cons_[stage] + o * (stage == "geometric source terms" ? 4 : ncons);
   return rc;

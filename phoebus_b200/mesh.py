@@ -294,38 +294,52 @@ class MeshPack:
         self.pack = pk
         self.flags_valid = False
 
-    def ghost_plan_host(self):
-        """(mask [nblocks*ncell] u8, ids of the ghost zones that keep their own con2prim u32) of pb_ghost_plan_host for
-        this pack — host arrays only"""
+    def ghost_plan_host(self, twins=True):
+        """(mask [nblocks*ncell] u8: 1 deferred, 2 twin; ids of the ghost zones that keep their own con2prim u32; ids of the
+        twin zones u32) of pb_ghost_plan_host for this pack — host arrays only"""
         L = _lib.lib()
         nint = self.nx[0] * (self.nx[1] if self.ndim >= 2 else 1) * (self.nx[2] if self.ndim >= 3 else 1)
         mask = np.zeros(self.nblocks * self.ncell, dtype=np.uint8)
         zones = np.zeros(max(1, self.nblocks * (self.ncell - nint)), dtype=np.uint32)
-        n = C.c_longlong(0)
+        n, nt = C.c_longlong(0), C.c_longlong(0)
         cfg = self.p.make_cfg(self.gshape)
+        tw = np.zeros(max(1, int(L.pb_twin_entries(C.byref(cfg), self.nblocks))), dtype=np.uint32)
         _lib.check(L.pb_ghost_plan_host(C.byref(cfg), C.addressof(self.blocks_host), self.nblocks, self.geom_host.ctypes.data,
-                                        self.floor_host.ctypes.data, mask.ctypes.data, zones.ctypes.data, C.byref(n)),
+                                        self.floor_host.ctypes.data, mask.ctypes.data, zones.ctypes.data, C.byref(n),
+                                        tw.ctypes.data if twins else None, C.byref(nt) if twins else None),
                    "pb_ghost_plan_host")
-        return mask, zones[:n.value].copy()
+        return mask, zones[:n.value].copy(), tw[:nt.value].copy()
 
     def _ghost_plan(self, pk):
-        """which ghost zones take their con2prim result from the same-GPU neighbour instead of solving again
-        (pb_ghost_plan_host, csrc/ghost_plan_host.cpp); use_ghost_plan=False leaves the pack without a plan"""
+        """which ghost zones take their con2prim result from the same-GPU neighbour instead of solving again, and which are
+        solved as twins in a side buffer (pb_ghost_plan_host, csrc/ghost_plan_host.cpp); use_ghost_plan=False leaves the pack
+        without a plan, use_ghost_plan="notwins" without the twin part"""
         t = self.torch
-        self.ghost_mask = self.c2p_zones = None
-        self.n_deferred, self.n_c2p_zones = 0, self.nblocks * self.ncell
+        self.ghost_mask = self.c2p_zones = self.twin_zones = None
+        self.n_deferred, self.n_twin, self.n_c2p_zones = 0, 0, self.nblocks * self.ncell
         if not self.use_ghost_plan or not self.p.bc_prim:
             return
-        mask, zones = self.ghost_plan_host()
-        self.n_deferred = int(mask.sum())
-        if self.n_deferred == 0:
+        import os
+        mask, zones, tw = self.ghost_plan_host(twins=self.use_ghost_plan != "notwins" and os.environ.get("PB_GHOST_TWINS", "1") != "0")
+        self.n_deferred = int((mask == 1).sum())
+        self.n_twin = len(tw)
+        if self.n_deferred == 0 and self.n_twin == 0:
             return
-        self.n_c2p_zones = self.zones() + len(zones)  # interiors + the listed ghost zones
+        self.n_c2p_zones = self.zones() + len(zones) + len(tw)  # interiors + the listed ghost zones + the twins
         self.ghost_mask = t.from_numpy(mask).to(self.device)
         self.c2p_zones = t.from_numpy(zones if len(zones) else np.zeros(1, dtype=np.uint32)).to(self.device)
         pk.ghost_mask = self.ghost_mask.data_ptr()
         pk.c2p_zones = self.c2p_zones.data_ptr()
         pk.n_c2p_zones = len(zones)
+        if self.n_twin:
+            S = int(_lib.lib().pb_twin_entries(C.byref(self.p.make_cfg(self.gshape)), self.nblocks))
+            self.twin_zones = t.from_numpy(tw).to(self.device)
+            self.twin_buf = t.zeros((self.ncons + self.nprim + 3 + self.ndim, S), dtype=t.float64, device=self.device)
+            self.twin_flags = t.zeros(S, dtype=t.uint8, device=self.device)
+            pk.twin_zones = self.twin_zones.data_ptr()
+            pk.n_twin = self.n_twin
+            pk.twin_buf = self.twin_buf.data_ptr()
+            pk.twin_flags = self.twin_flags.data_ptr()
 
     def zones(self):
         """interior zones owned by this pack"""

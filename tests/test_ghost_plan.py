@@ -14,7 +14,8 @@ PRIM_BC = ["torus2d", "torus3d", "torus2d_fail", "torus2d_polar", "reflect2d_pri
 def _plan(name):
     g, p = load_case(name)
     mesh, fp = product_mesh(g, alloc_fields=False)
-    mask, zones = mesh.ghost_plan_host()
+    mask, zones, twins = mesh.ghost_plan_host()
+    mesh.plan_twins = twins
     return g, mesh, fp, mask.reshape((mesh.nblocks,) + mesh.shape), zones
 
 
@@ -43,14 +44,21 @@ def test_plan_is_a_partition_and_respects_the_conditions(name):
     # interior zones + listed ghost zones + deferred ghost zones = every zone exactly once
     seen = np.tile((~ghost).reshape(-1).astype(np.int32), mesh.nblocks)
     np.add.at(seen, zones.astype(np.int64), 1)
-    assert np.array_equal(seen + mask.reshape(-1), np.ones(tot, dtype=np.int32))
+    assert np.array_equal(seen + (mask.reshape(-1) != 0), np.ones(tot, dtype=np.int32))
     assert np.all(np.diff(zones.astype(np.int64)) > 0)
+    # twins: exactly the zones with mask value 2, all of them x1 ghost zones; without the twin part they are ordinary listed zones
+    tw = mesh.plan_twins.astype(np.int64)
+    assert sorted(tw.tolist()) == np.nonzero(mask.reshape(-1) == 2)[0].tolist()
+    assert (o1.reshape(-1)[tw % ncell] != 0).all()
+    mask0, zones0, tw0 = mesh.ghost_plan_host(twins=False)
+    assert len(tw0) == 0 and np.array_equal(mask0 == 1, mask.reshape(-1) == 1) and not (mask0 == 2).any()
+    assert sorted(zones0.tolist()) == sorted(zones.tolist() + tw.tolist())
     if not fp.bc_prim:
         assert mask.sum() == 0
         return
     for n in range(mesh.nblocks):
         blk = mesh.blocks_host[n]
-        m = mask[n].astype(bool)
+        m = mask[n] != 0
         assert not (m & ~ghost).any()  # interior zones always solve
         for d, o in enumerate((o1, o2, o3)):
             if d >= mesh.ndim:
@@ -69,7 +77,7 @@ def test_reference_dumps_hold_the_neighbours_result_in_every_deferred_zone(name)
     g, mesh, fp, mask, zones = _plan(name)
     if mesh.nblocks == 1 and mask.sum() == 0:
         pytest.skip("single MeshBlock without a same-pack neighbour")
-    assert mask.sum() > 0, "fixture has neighbouring MeshBlocks but no deferred zone"
+    assert (mask == 1).sum() > 0, "fixture has neighbouring MeshBlocks but no deferred zone"
     _, code, src = _offsets(mesh)
     checked = 0
     for tag in stage_tags(g):
@@ -81,7 +89,7 @@ def test_reference_dumps_hold_the_neighbours_result_in_every_deferred_zone(name)
             ref = fd.ref_state(get, mb["gid"], mesh.shape, man["sc1"])
             state[n] = {k: np.asarray(v).reshape((-1, mesh.ncell)) for k, v in ref.items()}
         for n in range(mesh.nblocks):
-            m = mask[n].reshape(-1).astype(bool)
+            m = mask[n].reshape(-1) == 1  # (twin zones hold their OWN result: not the neighbour's bits)
             if not m.any():
                 continue
             nb = np.array([mesh.blocks_host[n].nbr[c] for c in range(27)])[code.reshape(-1)[m]]
