@@ -50,6 +50,16 @@ def test_plan_is_a_partition_and_respects_the_conditions(name):
     tw = mesh.plan_twins.astype(np.int64)
     assert sorted(tw.tolist()) == np.nonzero(mask.reshape(-1) == 2)[0].tolist()
     assert (o1.reshape(-1)[tw % ncell] != 0).all()
+    # list order (block, x1 ghost column, k, j) = increasing slot of the side buffer; slots are unique and inside the buffer
+    if len(tw):
+        from phoebus_b200 import _lib
+        import ctypes as C
+        S = int(_lib.lib().pb_twin_entries(C.byref(fp.make_cfg(mesh.gshape)), mesh.nblocks))
+        tb, tc = tw // ncell, tw % ncell
+        ti, tj, tk = tc % mesh.shape[2], (tc // mesh.shape[2]) % mesh.shape[1], tc // (mesh.shape[2] * mesh.shape[1])
+        col = np.where(ti < mesh.ng, ti, ti - mesh.nx[0])
+        slot = ((tb * 2 * mesh.ng + col) * mesh.shape[0] + tk) * mesh.shape[1] + tj
+        assert np.all(np.diff(slot) > 0) and slot[-1] < S and (col >= 0).all() and (col < 2 * mesh.ng).all()
     mask0, zones0, tw0 = mesh.ghost_plan_host(twins=False)
     assert len(tw0) == 0 and np.array_equal(mask0 == 1, mask.reshape(-1) == 1) and not (mask0 == 2).any()
     assert sorted(zones0.tolist()) == sorted(zones.tolist() + tw.tolist())
