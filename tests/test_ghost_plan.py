@@ -115,3 +115,34 @@ def test_reference_dumps_hold_the_neighbours_result_in_every_deferred_zone(name)
                     assert np.array_equal(a.view(np.int64), b.view(np.int64)), (name, tag, n, int(q), k)
                 checked += int(good.sum())
     assert checked > 0
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_remote_faces_are_never_deferred_in_a_brick_decomposition(world):
+    """one rank's brick of the 3-D torus (8 x 4 x 4 MeshBlocks of 16 x 8 x 8 over `world` GPUs): ghost zones whose source
+    block lives on another GPU arrive by NCCL after con2prim could have used them — neither deferred nor twins; the
+    interior faces of the brick still are"""
+    from phoebus_b200 import _lib
+    from phoebus_b200.mesh import MeshPack
+    g, p = load_case("torus3d")
+    from phoebus_b200.params import FluidParams, ParameterInput
+    pin = ParameterInput.from_blocks(g.meta["deck_blocks"])
+    for k, v in g.manifest("init")["mesh"].items():
+        pin.blocks.setdefault("parthenon/mesh", {})[k] = repr(float(v))
+    pin.blocks.setdefault("geometry", {})["kind"] = "fmks"
+    pin.blocks["parthenon/mesh"].update(nx1="128", nx2="32", nx3="32")
+    fp = FluidParams(pin)
+    seen_remote = seen_deferred = 0
+    for rank in range(world):
+        mesh = MeshPack(fp, device=None, rank=rank, world=world, alloc_fields=False)
+        mask, zones, twins = mesh.ghost_plan_host()
+        mask = mask.reshape((mesh.nblocks,) + mesh.shape)
+        (o1, o2, o3), code, src = _offsets(mesh)
+        for n in range(mesh.nblocks):
+            nb = np.array([mesh.blocks_host[n].nbr[c] for c in range(27)])[code]
+            remote = nb == _lib.PB_NBR_REMOTE
+            seen_remote += int(remote.sum())
+            assert not mask[n][remote].any()
+            assert (nb[mask[n] != 0] >= 0).all()
+        seen_deferred += int((mask == 1).sum())
+    assert seen_remote > 0 and seen_deferred > 0
