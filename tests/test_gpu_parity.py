@@ -825,8 +825,8 @@ def _torus_run(block, mesh_nx, cycles, use_ghost_plan, force_split=False, graphs
 
 @pytest.mark.parametrize("force_split", [False, True])
 def test_ghost_plan_on_a_mesh_with_inner_blocks_changes_no_bit(force_split):
-    """64 MeshBlocks of 16^3 (8 of them away from every mesh boundary, so all three segments of the plan's zone list are
-    populated): two cycles with the ghost plan equal two cycles without it in every field of every zone, ghosts
+    """64 MeshBlocks of 16^3 (8 of them away from every mesh boundary, so the early con2prim of the inner blocks, the listed
+    ghost zones and the twins are all exercised): two cycles with the ghost plan equal two cycles without it in every field of every zone, ghosts
     included, and in the floor / failure counters; also with con2prim split around the (here empty) transfer"""
     ref, mref = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=False)
     out, mesh = _torus_run(16, (64, 64, 64), 2, use_ghost_plan=True, force_split=force_split)
